@@ -1,0 +1,131 @@
+/*
+ * pwa.h -- C ABI of the B200-native prompted 3D shifted-window attention path.
+ *
+ * The reference (liamliaw/medical-image-segmentation-with-visual-prompts) is pure Python and
+ * has no FFI of its own; its boundary for this path is the nn.Module API of
+ *   src/modules/swin_transformer/swin_block.py      (SwinTransformerBlock, ConsecutiveSwinBlocks,
+ *                                                     window_partition, window_reverse, get_attn_mask)
+ *   src/modules/multi_head_attention/window_attention.py            (WindowAttention)
+ *   src/modules/multi_head_attention/relative_positional_encoding.py (RelativePE)
+ * The Python mirror of those classes in this repo calls the entry points below through ctypes
+ * (see INTEGRATION.md for the binding a reference maintainer would add).  Each entry point names the
+ * reference lines it replaces.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.
+ *   - every device buffer is allocated by the caller; nothing here allocates, frees or synchronises.
+ *   - every launch goes to the cudaStream_t passed in (void* so that C callers need no CUDA headers).
+ *   - return 0 on success, <0 on error; pwa_last_error() returns a thread-local message.
+ *   - the device is the caller's current device (one process per GPU).
+ *   - re-entrant and thread-safe (no global mutable state besides one-time kernel attribute setup).
+ *   - there is NO CPU fallback: device entry points fail with PWA_ERR_CUDA when no GPU is present.
+ */
+#ifndef PWA_H_
+#define PWA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PWA_VERSION 100
+
+enum { PWA_OK = 0, PWA_ERR_ARG = -1, PWA_ERR_UNSUPPORTED = -2, PWA_ERR_CUDA = -3 };
+enum { PWA_F32 = 0, PWA_BF16 = 1 };
+
+/* Window geometry of one block call.  Filled by pwa_geometry(); plain ints so that it can be
+ * mirrored by a ctypes.Structure. */
+typedef struct pwa_geom {
+  int32_t dims[3];      /* H, W, D of the unpadded feature map                                      */
+  int32_t ws[3];        /* window (wh, ww, wd)                                                      */
+  int32_t shift[3];     /* effective shift, 0 where dims[a] <= ws[a]         (swin_block.py:265-270) */
+  int32_t pads[6];      /* the reference's `paddings` (floor,ceil per axis)  (swin_block.py:150-161) */
+  int32_t sp[3];        /* padded dims = dims + pads                                                */
+  int32_t nwin[3];      /* P1,P2,P3 = sp / ws                                                       */
+  int32_t data_lo[3];   /* low-side zero padding of the DATA = pads[2a+1] (F.pad(reversed), :163)    */
+  int32_t crop_lo[3];   /* low-side offset of the output crop / mask box = pads[2a] (:247-253)       */
+  int32_t P;            /* windows per sample                                                       */
+  int32_t N;            /* tokens per window                                                        */
+  int32_t masked;       /* 1 iff any shift > 0 (a shift mask exists, :173)                          */
+  int32_t padded;       /* 1 iff any pad > 0                                                        */
+} pwa_geom;
+
+/* ---- host-only helpers (no GPU needed) ------------------------------------------------------ */
+
+int pwa_version(void);
+const char* pwa_last_error(void);
+
+/* swin_block.py:146-164, 265-270: padding rule, effective shift, window counts. */
+int pwa_geometry(const int32_t dims[3], const int32_t ws[3], const int32_t shift_cfg[3], pwa_geom* out);
+
+/* swin_block.py:312-364 (get_attn_mask) in compressed form: one region id per (window, token),
+ * uint8 [P][N] written to HOST memory; mask[p][i][j] == 1.0f iff ids[p][i] == ids[p][j].
+ * ids are 9*rh+3*rw+rd (0..26) or 100 inside the un-padded box when the map is padded. */
+int pwa_region_ids(const pwa_geom* g, uint8_t* ids_host);
+
+/* flat source index (into the unpadded H*W*D volume, -1 = zero padding) of every (window, token):
+ * int32 [P][N] to HOST memory.  which = 0: input side (pad -> roll -> window_partition,
+ * swin_block.py:163,174-178,292-299); which = 1: output side (window_reverse -> roll back -> crop,
+ * swin_block.py:302-309,238-253). */
+int pwa_index_map(const pwa_geom* g, int which, int32_t* map_host);
+
+/* ---- (a) cyclic roll + pad + strided window partition / reverse ------------------------------ */
+
+/* x [B][C][H][W][D] -> tokens [B][P][N][C].  lo = g->data_lo when (use_crop_lo & 1) == 0 (forward of the
+ * block input), g->crop_lo when 1 (adjoint of pwa_reverse).  Replaces F.pad + torch.roll +
+ * window_partition + rearrange (swin_block.py:163,174-178,205,209,214).
+ * Bit 1 of use_crop_lo forces the element-wise generic kernel (checker for the staged fast kernel). */
+int pwa_partition(const void* x, void* tokens, int B, int C, const pwa_geom* g, int use_crop_lo,
+                  int dtype, void* stream);
+
+/* tokens [B][P][N][C] -> x [B][C][H][W][D]; exact inverse index map incl. roll back and crop.
+ * use_crop_lo == 1 for the block output (swin_block.py:228-253), 0 for the adjoint of
+ * pwa_partition.  Token slots that map to padding are dropped. */
+int pwa_reverse(const void* tokens, void* x, int B, int C, const pwa_geom* g, int use_crop_lo,
+                int dtype, void* stream);
+
+/* ---- (b) fused prompted window attention, forward -------------------------------------------- */
+
+typedef struct pwa_attn_shape {
+  int32_t B, P, C, heads, I;   /* I = number of prompt tokens (0 = none)           */
+  int32_t ws[3];               /* N = ws[0]*ws[1]*ws[2]                            */
+  float scale;                 /* head_dim ** -0.5  (window_attention.py:25)       */
+  float p_drop;                /* attention dropout probability (0 in eval)        */
+  uint64_t seed, offset;       /* Philox key/counter taken from torch's generator  */
+} pwa_attn_shape;
+
+/* q,k,v [B][P][N][C]; kp,vp [B][I][C] (NULL when I == 0): keys/values of the prompt tokens,
+ * shared by every window of a sample; th [h][wh][wh], tw [h][ww][ww], td [h][wd][wd], tok [h][I]:
+ * fp32 bias tables INCLUDING the /3 and embed_dim**-0.5 factors
+ * (relative_positional_encoding.py:116-123,136-138); ids uint8 [P][N] on the DEVICE or NULL (no
+ * shift mask).  out [B][P][N][C]; lse fp32 [B][P][h][N] (natural-log sum-exp of the masked logits).
+ * logits = (q.k^T*scale + bias) * mask ; softmax ; dropout ; @ v   (window_attention.py:49-58),
+ * queries = the N content tokens only (prompt rows are cut by swin_block.py:222-225).
+ * impl: 0 = auto, 1 = fp32 CUDA-core kernel, 2 = bf16 tcgen05/TMEM kernel. */
+int pwa_attn_fwd(const void* q, const void* k, const void* v, const void* kp, const void* vp,
+                 const float* th, const float* tw, const float* td, const float* tok,
+                 const uint8_t* ids, void* out, float* lse, const pwa_attn_shape* s, int dtype,
+                 int impl, void* stream);
+
+/* ---- (c) backward ----------------------------------------------------------------------------- */
+
+/* Inputs as pwa_attn_fwd plus out, lse, dout [B][P][N][C].  Outputs: dq,dk,dv [B][P][N][C] (dtype);
+ * dkp,dvp fp32 [B][I][C], summed over the P windows of each sample; dth,dtw,dtd,dtok fp32, summed
+ * over batch and windows.  The fp32 accumulators are zeroed by this call (cudaMemsetAsync on
+ * `stream`).  delta fp32 [B][P][h][N] is caller-provided scratch. */
+int pwa_attn_bwd(const void* q, const void* k, const void* v, const void* kp, const void* vp,
+                 const float* th, const float* tw, const float* td, const float* tok,
+                 const uint8_t* ids, const void* out, const float* lse, const void* dout,
+                 void* dq, void* dk, void* dv, float* dkp, float* dvp,
+                 float* dth, float* dtw, float* dtd, float* dtok, float* delta,
+                 const pwa_attn_shape* s, int dtype, int impl, void* stream);
+
+/* 1 iff the bf16 tcgen05 kernel supports this shape (else impl=0 falls back to the fp32-math kernel). */
+int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PWA_H_ */

@@ -1,0 +1,75 @@
+"""ctypes binding of libpwa_b200.so (C ABI in include/pwa.h).
+
+There is NO CPU fallback and no alternative backend: if the shared library is missing the
+import fails loudly with the build command; device entry points raise on a machine without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpwa_b200.so")
+
+PWA_F32, PWA_BF16 = 0, 1
+
+
+class PwaGeom(C.Structure):
+    _fields_ = [
+        ("dims", C.c_int32 * 3), ("ws", C.c_int32 * 3), ("shift", C.c_int32 * 3), ("pads", C.c_int32 * 6),
+        ("sp", C.c_int32 * 3), ("nwin", C.c_int32 * 3), ("data_lo", C.c_int32 * 3), ("crop_lo", C.c_int32 * 3),
+        ("P", C.c_int32), ("N", C.c_int32), ("masked", C.c_int32), ("padded", C.c_int32),
+    ]
+
+
+class PwaAttnShape(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("I", C.c_int32),
+        ("ws", C.c_int32 * 3), ("scale", C.c_float), ("p_drop", C.c_float),
+        ("seed", C.c_uint64), ("offset", C.c_uint64),
+    ]
+
+
+class PwaError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension is not built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` (or `make -C <package>/csrc`). "
+            "This package has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, f32p, u8p = C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p
+    gp, sp = C.POINTER(PwaGeom), C.POINTER(PwaAttnShape)
+    lib.pwa_version.restype = i32
+    lib.pwa_last_error.restype = C.c_char_p
+    lib.pwa_geometry.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), gp]
+    lib.pwa_region_ids.argtypes = [gp, vp]
+    lib.pwa_index_map.argtypes = [gp, i32, vp]
+    lib.pwa_partition.argtypes = [vp, vp, i32, i32, gp, i32, i32, vp]
+    lib.pwa_reverse.argtypes = [vp, vp, i32, i32, gp, i32, i32, vp]
+    lib.pwa_attn_tc_supported.argtypes = [sp, i32]
+    lib.pwa_attn_fwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, sp, i32, i32, vp]
+    lib.pwa_attn_bwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, vp] + [vp] * 3 + [f32p] * 7 + [sp, i32, i32, vp]
+    for name in ("pwa_geometry", "pwa_region_ids", "pwa_index_map", "pwa_partition", "pwa_reverse",
+                 "pwa_attn_tc_supported", "pwa_attn_fwd", "pwa_attn_bwd"):
+        getattr(lib, name).restype = i32
+    return lib
+
+
+lib = _load()
+
+EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
+                    "pwa_partition", "pwa_reverse", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported")
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib.pwa_last_error().decode("utf-8", "replace")
+        if rc == -1 and "not compatible with the number of heads" in msg:
+            raise ValueError(msg)                      # same exception type as window_attention.py:19-22
+        if rc == -2:
+            raise NotImplementedError(f"{what}: {msg}")
+        raise PwaError(f"{what} failed (rc={rc}): {msg}")

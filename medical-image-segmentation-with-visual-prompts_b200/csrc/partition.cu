@@ -1,0 +1,356 @@
+// (a) pad + cyclic roll + strided window partition / reverse for channels-first 3D feature maps.
+//
+// Replaces F.pad + torch.roll + einops window_partition + 'b p c h w d -> b p (h w d) c'
+// (reference swin_transformer/swin_block.py:163,174-178,205-214) and its inverse
+// (window_reverse + roll back + crop, :228-253).  Pure byte movement: bit-exact by construction.
+//
+// Layouts:  x      [B][C][H][W][D]            (D contiguous)
+//           tokens [B][P][N][C]               (C contiguous), P = P1*P2*P3 windows, N = wh*ww*wd
+// Window (p1,p2,p3) / token (t1,t2,t3) sits at rolled-frame coordinate (t_a*P_a + p_a) -- windows
+// are STRIDED -- which is padded-frame coordinate (r + shift) mod Sp and unpadded r' = that - lo.
+//
+// Fast kernel: one CTA owns a (batch, rolled h coordinate, window column p2, channel chunk) slab,
+// i.e. ww lines of the padded map x CT channels.  It is staged through shared memory as
+// S[w'][rolled d][channel word] so that BOTH global sides are fully coalesced: the x side moves
+// whole D-lines, the token side moves runs of ww*wd*CT contiguous elements per window.
+// All traffic is 32-bit words (one fp32 or a pair of bf16 channels); bf16 needs a 2x2 in-register
+// transpose (PRMT) because x is contiguous along D and tokens along C.
+#include "common.cuh"
+
+namespace pwa {
+
+struct PartParams {
+  int B, C;
+  int H, W, D;
+  int Hp, Wp, Dp;
+  int P1, P2, P3;
+  int wh, ww, wd;
+  int sh, sw, sd;
+  int loh, low, lod;
+  int N, P;
+  int CT;        // channels per CTA chunk
+  int nchunk;    // C / CT
+  int pitch;     // smem row pitch in 32-bit words (odd)
+  int padded;
+  FastDiv div_cw, div_wwwd, div_wd, div_dq, div_ww;
+};
+
+// ---------------------------------------------------------------------------------------------
+// generic element-wise kernels (any shape / alignment).  Also the on-GPU checker of the fast path.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void partition_generic_kernel(const T* __restrict__ x, T* __restrict__ tok, PartParams p, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % p.C);
+    size_t r = i / p.C;
+    int n = (int)(r % p.N);
+    r /= p.N;
+    int win = (int)(r % p.P);
+    int b = (int)(r / p.P);
+    int t3 = n % p.wd, t2 = (n / p.wd) % p.ww, t1 = n / (p.wd * p.ww);
+    int p3 = win % p.P3, p2 = (win / p.P3) % p.P2, p1 = win / (p.P3 * p.P2);
+    int h = (t1 * p.P1 + p1 + p.sh) % p.Hp - p.loh;
+    int w = (t2 * p.P2 + p2 + p.sw) % p.Wp - p.low;
+    int d = (t3 * p.P3 + p3 + p.sd) % p.Dp - p.lod;
+    T v = T(0);
+    if (h >= 0 && h < p.H && w >= 0 && w < p.W && d >= 0 && d < p.D)
+      v = x[(((size_t)b * p.C + c) * p.H + h) * p.W * p.D + (size_t)w * p.D + d];
+    tok[i] = v;
+  }
+}
+
+template <typename T>
+__global__ void reverse_generic_kernel(const T* __restrict__ tok, T* __restrict__ x, PartParams p, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    int d = (int)(i % p.D);
+    size_t r = i / p.D;
+    int w = (int)(r % p.W);
+    r /= p.W;
+    int h = (int)(r % p.H);
+    r /= p.H;
+    int c = (int)(r % p.C);
+    int b = (int)(r / p.C);
+    // unpadded -> padded -> rolled frame (inverse of roll(-s))
+    int rh = (h + p.loh - p.sh + p.Hp) % p.Hp;
+    int rw = (w + p.low - p.sw + p.Wp) % p.Wp;
+    int rd = (d + p.lod - p.sd + p.Dp) % p.Dp;
+    int t1 = rh / p.P1, p1 = rh % p.P1;
+    int t2 = rw / p.P2, p2 = rw % p.P2;
+    int t3 = rd / p.P3, p3 = rd % p.P3;
+    int win = (p1 * p.P2 + p2) * p.P3 + p3;
+    int n = (t1 * p.ww + t2) * p.wd + t3;
+    x[i] = tok[(((size_t)b * p.P + win) * p.N + n) * p.C + c];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fast kernels
+// ---------------------------------------------------------------------------------------------
+// EB = element bytes (2: bf16, words hold two adjacent channels; 4: fp32).
+// grid.x = B * Hp * P2 * nchunk ; block = 256 threads ; dynamic smem = ww * Dp * pitch * 4 bytes.
+template <int EB>
+struct Slab {
+  int b, a, p2, chunk;      // a = rolled h coordinate
+  int t1, p1;               // a = t1 * P1 + p1
+  int h;                    // source row in the unpadded map (may be out of range)
+  __device__ __forceinline__ Slab(const PartParams& p) {
+    uint32_t r = blockIdx.x;
+    chunk = r % p.nchunk;
+    r /= p.nchunk;
+    p2 = r % p.P2;
+    r /= p.P2;
+    a = r % p.Hp;
+    b = r / p.Hp;
+    t1 = a / p.P1;
+    p1 = a - t1 * p.P1;
+    h = (a + p.sh) % p.Hp - p.loh;
+  }
+};
+
+__device__ __forceinline__ int roll_fwd(int d, int lo, int s, int S) {  // unpadded -> rolled frame
+  int r = d + lo - s;
+  r += (r < 0) ? S : 0;
+  r -= (r >= S) ? S : 0;
+  return r;
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) partition_fast_kernel(const uint32_t* __restrict__ x, uint32_t* __restrict__ tok,
+                                                             PartParams p) {
+  extern __shared__ uint32_t smem[];
+  const Slab<EB> s(p);
+  const int tid = threadIdx.x;
+  constexpr int EPW = 4 / EB;              // elements per word
+  const int CW = p.CT / EPW;               // channel words per token in this chunk
+  const int rows = p.ww * p.Dp;
+
+  if (p.padded) {  // slots that no source voxel reaches must read as zero padding
+    for (int i = tid; i < rows * p.pitch; i += 256) smem[i] = 0u;
+    __syncthreads();
+  }
+
+  // ---- phase 1: x lines -> smem.  item = (channel word, w', d word), d fastest (coalesced) ----
+  const bool h_ok = s.h >= 0 && s.h < p.H;
+  if (h_ok) {
+    const int DQ = p.D / EPW;  // words per D line
+    const int items = CW * p.ww * DQ;
+    const size_t plane = (size_t)p.H * p.W * p.D;  // elements per channel
+    const size_t base_b = ((size_t)s.b * p.C + (size_t)s.chunk * p.CT) * plane + (size_t)s.h * p.W * p.D;
+#pragma unroll 4
+    for (int i = tid; i < items; i += 256) {
+      uint32_t line, dq, cw, t2;
+      p.div_dq.divmod(i, line, dq);
+      p.div_ww.divmod(line, cw, t2);
+      int w = (int)(t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      if (w < 0 || w >= p.W) continue;
+      if (EB == 4) {
+        size_t g = base_b + (size_t)cw * plane + (size_t)w * p.D + dq;
+        uint32_t v = __ldg(x + g);
+        int r = roll_fwd(dq, p.lod, p.sd, p.Dp);
+        smem[(t2 * p.Dp + r) * p.pitch + cw] = v;
+      } else {
+        // two bf16 channels (2cw, 2cw+1) x two d positions (2dq, 2dq+1): 2x2 transpose in registers
+        size_t g0 = base_b + (size_t)(2 * cw) * plane + (size_t)w * p.D + 2 * dq;  // element offset, even
+        uint32_t v0 = __ldg(x + (g0 >> 1));
+        uint32_t v1 = __ldg(x + ((g0 + plane) >> 1));
+        uint32_t lo = __byte_perm(v0, v1, 0x5410);  // (c0,d0),(c1,d0)
+        uint32_t hi = __byte_perm(v0, v1, 0x7632);  // (c0,d1),(c1,d1)
+        int r0 = roll_fwd(2 * dq, p.lod, p.sd, p.Dp);
+        int r1 = roll_fwd(2 * dq + 1, p.lod, p.sd, p.Dp);
+        smem[(t2 * p.Dp + r0) * p.pitch + cw] = lo;
+        smem[(t2 * p.Dp + r1) * p.pitch + cw] = hi;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: smem -> tokens.  item = (p3, w', d', channel word), channel fastest ----
+  {
+    const int per_win = p.ww * p.wd * CW;
+    const int items = p.P3 * per_win;
+    const size_t tok_stride_w = (size_t)p.C / EPW;  // words per token
+    const size_t win0 = ((size_t)s.b * p.P + ((size_t)s.p1 * p.P2 + s.p2) * p.P3);
+    const size_t row0 = (size_t)s.t1 * p.ww * p.wd;  // first token of this h' row inside a window
+    const size_t cw0 = (size_t)s.chunk * CW;
+#pragma unroll 4
+    for (int i = tid; i < items; i += 256) {
+      uint32_t p3, rem, tk, cw, t2, t3;
+      p.div_cw.divmod(i, tk, cw);          // tk = (p3, w', d') flattened
+      p.div_wwwd.divmod(tk, p3, rem);
+      p.div_wd.divmod(rem, t2, t3);
+      uint32_t v = smem[(t2 * p.Dp + t3 * p.P3 + p3) * p.pitch + cw];
+      size_t g = ((win0 + p3) * p.N + row0 + rem) * tok_stride_w + cw0 + cw;
+      tok[g] = v;
+    }
+  }
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) reverse_fast_kernel(const uint32_t* __restrict__ tok, uint32_t* __restrict__ x,
+                                                           PartParams p) {
+  extern __shared__ uint32_t smem[];
+  const Slab<EB> s(p);
+  const int tid = threadIdx.x;
+  constexpr int EPW = 4 / EB;
+  const int CW = p.CT / EPW;
+  const bool h_ok = s.h >= 0 && s.h < p.H;
+  if (!h_ok) return;  // this rolled row is cropped away entirely (uniform per CTA)
+
+  // ---- phase 1: tokens -> smem (channel fastest: coalesced) ----
+  {
+    const int per_win = p.ww * p.wd * CW;
+    const int items = p.P3 * per_win;
+    const size_t tok_stride_w = (size_t)p.C / EPW;
+    const size_t win0 = ((size_t)s.b * p.P + ((size_t)s.p1 * p.P2 + s.p2) * p.P3);
+    const size_t row0 = (size_t)s.t1 * p.ww * p.wd;
+    const size_t cw0 = (size_t)s.chunk * CW;
+#pragma unroll 4
+    for (int i = tid; i < items; i += 256) {
+      uint32_t p3, rem, tk, cw, t2, t3;
+      p.div_cw.divmod(i, tk, cw);
+      p.div_wwwd.divmod(tk, p3, rem);
+      p.div_wd.divmod(rem, t2, t3);
+      size_t g = ((win0 + p3) * p.N + row0 + rem) * tok_stride_w + cw0 + cw;
+      smem[(t2 * p.Dp + t3 * p.P3 + p3) * p.pitch + cw] = __ldg(tok + g);
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: smem -> x lines (d fastest: coalesced) ----
+  {
+    const int DQ = p.D / EPW;
+    const int items = CW * p.ww * DQ;
+    const size_t plane = (size_t)p.H * p.W * p.D;
+    const size_t base_b = ((size_t)s.b * p.C + (size_t)s.chunk * p.CT) * plane + (size_t)s.h * p.W * p.D;
+#pragma unroll 4
+    for (int i = tid; i < items; i += 256) {
+      uint32_t line, dq, cw, t2;
+      p.div_dq.divmod(i, line, dq);
+      p.div_ww.divmod(line, cw, t2);
+      int w = (int)(t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      if (w < 0 || w >= p.W) continue;
+      if (EB == 4) {
+        int r = roll_fwd(dq, p.lod, p.sd, p.Dp);
+        uint32_t v = smem[(t2 * p.Dp + r) * p.pitch + cw];
+        x[base_b + (size_t)cw * plane + (size_t)w * p.D + dq] = v;
+      } else {
+        int r0 = roll_fwd(2 * dq, p.lod, p.sd, p.Dp);
+        int r1 = roll_fwd(2 * dq + 1, p.lod, p.sd, p.Dp);
+        uint32_t lo = smem[(t2 * p.Dp + r0) * p.pitch + cw];  // (c0,d0),(c1,d0)
+        uint32_t hi = smem[(t2 * p.Dp + r1) * p.pitch + cw];  // (c0,d1),(c1,d1)
+        uint32_t v0 = __byte_perm(lo, hi, 0x5410);            // (c0,d0),(c0,d1)
+        uint32_t v1 = __byte_perm(lo, hi, 0x7632);            // (c1,d0),(c1,d1)
+        size_t g0 = base_b + (size_t)(2 * cw) * plane + (size_t)w * p.D + 2 * dq;
+        x[g0 >> 1] = v0;
+        x[(g0 + plane) >> 1] = v1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int fill_params(PartParams& p, int B, int C, const pwa_geom* g, int use_crop_lo, int eb, bool* fast) {
+  p.B = B; p.C = C;
+  p.H = g->dims[0]; p.W = g->dims[1]; p.D = g->dims[2];
+  p.Hp = g->sp[0]; p.Wp = g->sp[1]; p.Dp = g->sp[2];
+  p.P1 = g->nwin[0]; p.P2 = g->nwin[1]; p.P3 = g->nwin[2];
+  p.wh = g->ws[0]; p.ww = g->ws[1]; p.wd = g->ws[2];
+  p.sh = g->shift[0]; p.sw = g->shift[1]; p.sd = g->shift[2];
+  const int32_t* lo = (use_crop_lo & 1) ? g->crop_lo : g->data_lo;
+  p.loh = lo[0]; p.low = lo[1]; p.lod = lo[2];
+  p.N = g->N; p.P = g->P;
+  p.padded = g->padded;
+  const int epw = 4 / eb;
+  // fast path needs whole 32-bit words on both sides
+  bool ok = (C % epw == 0) && (p.D % epw == 0);
+  // channel chunk: largest divisor of C that is <= 64 and a whole number of words
+  int ct = 0;
+  for (int c = (C < 64 ? C : 64); c >= epw; --c)
+    if (C % c == 0 && c % epw == 0) { ct = c; break; }
+  if (ct == 0) ok = false;
+  if (ok) {
+    p.CT = ct;
+    p.nchunk = C / ct;
+    int cw = ct / epw;
+    p.pitch = cw | 1;  // odd word pitch: conflict-free for both access directions
+    size_t smem = (size_t)p.ww * p.Dp * p.pitch * 4;
+    size_t items = (size_t)p.P3 * p.ww * p.wd * cw;
+    if (smem > 200 * 1024 || items >= 65536 || (size_t)cw * p.ww * (p.D / epw) >= 65536) ok = false;
+    p.div_cw = FastDiv(cw);
+    p.div_wwwd = FastDiv(p.ww * p.wd);
+    p.div_wd = FastDiv(p.wd);
+    p.div_dq = FastDiv(p.D / epw);
+    p.div_ww = FastDiv(p.ww);
+  }
+  *fast = ok;
+  return 0;
+}
+
+template <int EB>
+static int launch_fast(bool is_partition, const void* src, void* dst, const PartParams& p, cudaStream_t st) {
+  size_t smem = (size_t)p.ww * p.Dp * p.pitch * 4;
+  dim3 grid((unsigned)((size_t)p.B * p.Hp * p.P2 * p.nchunk));
+  if (is_partition) {
+    static bool attr_done = false;  // benign race: idempotent
+    if (!attr_done) {
+      PWA_CUDA_OK(cudaFuncSetAttribute(partition_fast_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    partition_fast_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      PWA_CUDA_OK(cudaFuncSetAttribute(reverse_fast_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    reverse_fast_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
+  }
+  PWA_CUDA_OK(cudaGetLastError());
+  return PWA_OK;
+}
+
+template <typename T>
+static int launch_generic(bool is_partition, const void* src, void* dst, const PartParams& p, cudaStream_t st) {
+  size_t total = is_partition ? (size_t)p.B * p.P * p.N * p.C : (size_t)p.B * p.C * p.H * p.W * p.D;
+  if (total == 0) return PWA_OK;
+  unsigned blocks = (unsigned)((total + 255) / 256);
+  if (blocks > 148u * 32u) blocks = 148u * 32u;
+  if (is_partition)
+    partition_generic_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, (T*)dst, p, total);
+  else
+    reverse_generic_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, (T*)dst, p, total);
+  PWA_CUDA_OK(cudaGetLastError());
+  return PWA_OK;
+}
+
+static int run(bool is_partition, const void* src, void* dst, int B, int C, const pwa_geom* g, int use_crop_lo,
+               int dtype, void* stream) {
+  PWA_CHECK_ARG(src && dst && g, "pwa_partition/reverse: null pointer");
+  PWA_CHECK_ARG(B > 0 && C > 0, "pwa_partition/reverse: bad B=%d C=%d", B, C);
+  PWA_CHECK_ARG(dtype == PWA_F32 || dtype == PWA_BF16, "pwa_partition/reverse: bad dtype %d", dtype);
+  const int eb = dtype == PWA_F32 ? 4 : 2;
+  PartParams p;
+  bool fast = false;
+  fill_params(p, B, C, g, use_crop_lo, eb, &fast);
+  // `use_crop_lo & 2` forces the generic kernel (used by the tests to cross-check the fast path)
+  if (use_crop_lo & 2) fast = false;
+  if (((uintptr_t)src | (uintptr_t)dst) & 3) fast = false;  // fast path moves aligned 32-bit words
+  cudaStream_t st = (cudaStream_t)stream;
+  if (fast) return eb == 4 ? launch_fast<4>(is_partition, src, dst, p, st) : launch_fast<2>(is_partition, src, dst, p, st);
+  return eb == 4 ? launch_generic<uint32_t>(is_partition, src, dst, p, st)
+                 : launch_generic<uint16_t>(is_partition, src, dst, p, st);
+}
+
+}  // namespace pwa
+
+extern "C" int pwa_partition(const void* x, void* tokens, int B, int C, const pwa_geom* g, int use_crop_lo, int dtype,
+                             void* stream) {
+  return pwa::run(true, x, tokens, B, C, g, use_crop_lo, dtype, stream);
+}
+
+extern "C" int pwa_reverse(const void* tokens, void* x, int B, int C, const pwa_geom* g, int use_crop_lo, int dtype,
+                           void* stream) {
+  return pwa::run(false, tokens, x, B, C, g, use_crop_lo, dtype, stream);
+}

@@ -1,0 +1,64 @@
+"""Prompted multi-head window attention on the fused sm_100a kernels.
+
+Drop-in for the reference's WindowAttention (multi_head_attention/window_attention.py:11-61): same
+constructor, same parameters (`to_q/to_k/to_v` without bias, `proj` with bias), same ValueError for
+an incompatible head count.  The reference materialises the [B,P,h,N',N'] logits and makes ~10
+elementwise passes over them; here QK^T, bias, multiplicative shift mask, softmax and PV run inside
+one kernel (csrc/attn_*.cu) and only the N content tokens are queries (the reference cuts the prompt
+rows right after the residual, swin_block.py:222-225).
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import functional as PF
+
+
+class BiasTables(NamedTuple):
+    """Compact position bias (RelativePE.tables) + window shape."""
+    th: torch.Tensor
+    tw: torch.Tensor
+    td: torch.Tensor
+    tok: Optional[torch.Tensor]
+    ws: tuple
+
+
+class WindowAttention(nn.Module):
+    def __init__(self, dim: int, num_heads: int, attn_drop: float = 0.0, proj_drop: float = 0.0):
+        super().__init__()
+        if dim % num_heads != 0:
+            raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.to_q = nn.Linear(dim, dim, bias=False)
+        self.to_k = nn.Linear(dim, dim, bias=False)
+        self.to_v = nn.Linear(dim, dim, bias=False)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(proj_drop)
+        self.impl = PF.IMPL_AUTO
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias: Optional[BiasTables] = None,
+                mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None):
+        """q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
+        appended to the keys/values of every window; pos_bias: BiasTables; mask: uint8 region ids [P,N]
+        (mask[p,i,j] = ids[p,i]==ids[p,j]) or None.  Returns [B,P,N,C]."""
+        if pos_bias is None or not isinstance(pos_bias, BiasTables):
+            raise NotImplementedError("WindowAttention on the fused kernels takes the compact BiasTables form of the "
+                                      "position bias (RelativePE.tables), not a dense [1,1,h,N',N'] tensor")
+        if self.training and self.attn_drop.p > 0:
+            raise NotImplementedError("attn_drop > 0 in training mode is not implemented in the fused kernel yet")
+        dt = q.dtype
+        wq, wk, wv = (w.weight.to(dt) for w in (self.to_q, self.to_k, self.to_v))
+        qq, kk, vv = F.linear(q, wq), F.linear(k, wk), F.linear(v, wv)
+        kp = vp = None
+        if prompts is not None:
+            kp, vp = F.linear(prompts, wk), F.linear(prompts, wv)
+        o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
+                                         self.num_heads, pos_bias.ws, self.scale, self.impl)
+        o = F.linear(o, self.proj.weight.to(dt), self.proj.bias.to(dt))
+        return self.proj_drop(o)

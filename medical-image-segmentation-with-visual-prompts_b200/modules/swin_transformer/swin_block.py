@@ -1,0 +1,189 @@
+"""Prompted 3D shifted-window transformer block on hand-written sm_100a kernels.
+
+Drop-in for the reference's swin_transformer/swin_block.py: `ConsecutiveSwinBlocks` (:16-95),
+`SwinTransformerBlock` (:98-289) and the free functions `window_partition` (:292), `window_reverse`
+(:302), `get_attn_mask` (:312) keep their constructor arguments, forward(x, p) signatures, parameter
+names/shapes (state-dict compatible) and parameter-group accessors.
+
+What differs is HOW one block runs (reference forward_attn_mlp, :145-255):
+  reference: F.pad -> RelativePE dense bias -> torch.roll -> dense float mask [1,P,N',N'] -> rearrange ->
+             cat(prompts) per window -> LN -> 3 Linear -> bmm/softmax/bmm over [B,P,h,N',N'] -> ...
+  here:      ONE partition kernel (pad + roll + strided window gather + channels-last, csrc/partition.cu)
+             -> LN -> Linear -> ONE fused attention kernel (bias tables + uint8 region ids + softmax + PV,
+             prompt K/V computed once per sample instead of once per window, csrc/attn_*.cu)
+             -> proj/residual/LN/Linear -> ONE reverse kernel (window reverse + roll back + crop).
+Only the N content tokens are queries: the reference also pushes the I prompt rows of every window
+through attention and cuts them afterwards (:222-225), which cannot influence the output.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Sequence
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+import torch.utils.checkpoint as checkpoint
+
+from ... import functional as PF
+from ...geometry import get_geometry
+from ..multi_head_attention import BiasTables, RelativePE, WindowAttention
+from .down import PatchMerging
+
+
+class ConsecutiveSwinBlocks(nn.Module):
+    """Unshifted block, block shifted by window//2, optional PatchMerging (reference :16-71)."""
+
+    def __init__(self, hidden_channels: int, num_heads: int, pos_bias_embed_dim: int, max_prompts: int,
+                 tokens_per_prompt: int, window_size: Sequence[int], use_token_params: bool = True,
+                 shift_size: Sequence[int] = None, down: bool = True, merge_last_dim: bool = True,
+                 use_checkpoint: bool = False, out_channels: int = None, proj_drop: float = 0.0,
+                 attn_drop: float = 0.0):
+        super().__init__()
+        self.window_size = window_size
+        self.shift_size = tuple(s // 2 for s in window_size) if shift_size is None else shift_size
+        self.no_shift = tuple(0 for _ in window_size)
+        self.down = down
+        self.use_checkpoint = use_checkpoint
+        self.swin_blocks = nn.ModuleList([
+            SwinTransformerBlock(hidden_channels=hidden_channels, window_size=self.window_size,
+                                 pos_bias_embed_dim=pos_bias_embed_dim, num_heads=num_heads, max_prompts=max_prompts,
+                                 tokens_per_prompt=tokens_per_prompt, use_token_params=use_token_params,
+                                 shift_size=shift, attn_drop=attn_drop, proj_drop=proj_drop,
+                                 use_checkpoint=use_checkpoint)
+            for shift in (self.no_shift, self.shift_size)])
+        if down:
+            self.merge = PatchMerging(in_channels=hidden_channels,
+                                      out_channels=2 * hidden_channels if out_channels is None else out_channels,
+                                      merge_last_dim=merge_last_dim)
+
+    def forward(self, x, p=(None, None)):
+        for blk, prompt in zip(self.swin_blocks, p):
+            x = blk(x, prompt)
+        return self.merge(x) if self.down else x
+
+    def named_parameters_body(self):
+        out = [kv for blk in self.swin_blocks for kv in blk.named_parameters_body()]
+        if self.down:
+            out.extend(self.merge.named_parameters())
+        return out
+
+    def named_parameters_bias_content(self):
+        return [kv for blk in self.swin_blocks for kv in blk.named_parameters_bias_content()]
+
+    def named_parameters_bias_prompt_tokens(self):
+        return [kv for blk in self.swin_blocks for kv in blk.named_parameters_bias_prompt_tokens()]
+
+
+class SwinTransformerBlock(nn.Module):
+    def __init__(self, hidden_channels: int, window_size: Sequence[int], pos_bias_embed_dim: int, num_heads: int,
+                 max_prompts: int, tokens_per_prompt: int, use_token_params: bool = True,
+                 shift_size: Optional[Sequence[int]] = None, attn_drop: float = 0.0, proj_drop: float = 0.0,
+                 use_checkpoint: bool = False):
+        super().__init__()
+        self.num_heads = num_heads
+        self.window_size = window_size
+        self.shift_size = shift_size
+        self.use_checkpoint = use_checkpoint
+        # submodule creation order = reference order (:118-143), so seeded init is bit-identical
+        self.pe = RelativePE(embed_dim=pos_bias_embed_dim, num_heads=num_heads, max_abs_pos=window_size,
+                             max_cap_dist=window_size, max_prompts=max_prompts, tokens_per_prompt=tokens_per_prompt,
+                             use_token_params=use_token_params)
+        self.attn_norm = nn.LayerNorm(hidden_channels, eps=1e-6)
+        self.attn = WindowAttention(dim=hidden_channels, num_heads=num_heads, attn_drop=attn_drop, proj_drop=proj_drop)
+        self.mlp_norm = nn.LayerNorm(hidden_channels, eps=1e-6)
+        self.mlp = nn.Linear(hidden_channels, hidden_channels)    # the reference "MLP" is ONE Linear (:141-143)
+
+    def _compute_dtype(self, x):
+        if x.dtype == torch.bfloat16:
+            return torch.bfloat16
+        if torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16:
+            return torch.bfloat16
+        return torch.float32
+
+    def forward_attn_mlp(self, x, p=None):
+        if not x.is_cuda:
+            raise RuntimeError("pwa_b200.SwinTransformerBlock runs on CUDA (sm_100a) only; there is no CPU path")
+        ws = tuple(self.window_size)
+        shift_cfg = tuple(self.shift_size) if self.shift_size is not None else (0, 0, 0)
+        geom = get_geometry(tuple(x.shape[2:]), ws, shift_cfg)
+        cdt = self._compute_dtype(x)
+        in_dtype = x.dtype
+        n_prompt = 0 if p is None else p.size(1)
+        th, tw, td, tok = self.pe.tables(ws[0], ws[1], ws[2], n_prompt)
+        ids = geom.region_ids(x.device) if geom.masked else None
+
+        with torch.autocast('cuda', enabled=False):
+            xw = PF.partition_tokens(x.to(cdt), geom)                       # [B,P,N,C] = shortcut
+            c = xw.shape[-1]
+            nw, nb = self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt)
+            tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)
+            prompts = F.layer_norm(p.to(cdt), (c,), nw, nb, 1e-6) if p is not None else None
+            y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
+                          prompts=prompts)
+            y = y + xw
+            z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
+            y = y + F.linear(z, self.mlp.weight.to(cdt), self.mlp.bias.to(cdt))
+            out = PF.reverse_tokens(y, geom)                                # [B,C,H,W,D]
+        return out.to(in_dtype)
+
+    def forward(self, x, p=None):
+        if self.use_checkpoint:
+            return checkpoint.checkpoint(self.forward_attn_mlp, x, p, use_reentrant=False)
+        return self.forward_attn_mlp(x, p)
+
+    def get_shift_size(self, shape_x):
+        return tuple(0 if d <= w else s for d, w, s in zip(shape_x, self.window_size, self.shift_size))
+
+    def named_parameters_body(self):
+        return [*self.attn_norm.named_parameters(), *self.attn.named_parameters(),
+                *self.mlp_norm.named_parameters(), *self.mlp.named_parameters()]
+
+    def named_parameters_bias_content(self):
+        return [*self.pe.named_parameters_bias_content()]
+
+    def named_parameters_bias_prompt_tokens(self):
+        return [*self.pe.named_parameters_bias_prompt_tokens()]
+
+
+# --------------------------------------------------------------------------------------------------
+# free functions with the reference's signatures
+# --------------------------------------------------------------------------------------------------
+def window_partition(x, window_size):
+    """[b,c,H,W,D] -> [b,P,c,wh,ww,wd], strided windows (reference :292-299).  Dims must be divisible."""
+    ws = tuple(window_size)
+    geom = get_geometry(tuple(x.shape[2:]), ws, (0, 0, 0))
+    if geom.padded:
+        raise RuntimeError("window_partition: feature map not divisible by the window")
+    tok = PF.partition_tokens(x, geom)                                      # [b,P,N,c]
+    return tok.permute(0, 1, 3, 2).reshape(x.shape[0], geom.P, x.shape[1], *ws)
+
+
+def window_reverse(x, window_size, shape_x):
+    """[b,P,c,wh,ww,wd] -> [b,c,H,W,D] (reference :302-309)."""
+    ws = tuple(window_size)
+    geom = get_geometry(tuple(shape_x), ws, (0, 0, 0))
+    b, P, c = x.shape[:3]
+    tok = x.reshape(b, P, c, geom.N).permute(0, 1, 3, 2).contiguous()
+    return PF.reverse_tokens(tok, geom)
+
+
+def get_attn_mask(shape_x: Sequence[int], window_size: Sequence[int], shift_size: Sequence[int],
+                  paddings: Sequence[int], device: Optional[torch.device] = None):
+    """float32 [1,P,N,N] multiplicative shift mask (reference :312-364), expanded from the uint8 region
+    ids the kernels use.  `shape_x` is the PADDED shape and `paddings` the reference's floor/ceil list."""
+    from ... import _lib
+    import ctypes as C
+    import numpy as np
+    g = _lib.PwaGeom()
+    for a in range(3):
+        g.ws[a], g.shift[a], g.sp[a] = window_size[a], shift_size[a], shape_x[a]
+        g.pads[2 * a], g.pads[2 * a + 1] = paddings[2 * a], paddings[2 * a + 1]
+        g.nwin[a] = shape_x[a] // window_size[a]
+    g.P = g.nwin[0] * g.nwin[1] * g.nwin[2]
+    g.N = window_size[0] * window_size[1] * window_size[2]
+    g.padded = int(any(v > 0 for v in paddings))
+    ids = np.empty((g.P, g.N), dtype=np.uint8)
+    _lib.check(_lib.lib.pwa_region_ids(C.byref(g), ids.ctypes.data), "pwa_region_ids")
+    t = torch.from_numpy(ids).to(device if device is not None else 'cpu')
+    return (t[:, :, None] == t[:, None, :]).to(torch.float32).unsqueeze(0)

@@ -222,11 +222,15 @@ def run_ours(args):
     KernelStats.reset(enabled=True, timing=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         step_resident(i)
     e1.record()
     barrier()
+    if args.cuda_profiler_range:
+        torch.cuda.profiler.stop()
     ms = e0.elapsed_time(e1)
     launches = KernelStats.launches
     ksum = KernelStats.summary()
@@ -333,7 +337,7 @@ def _oracle_encoder(threads):
     return step
 
 
-def cpu_baseline_sample(steps=3, warmup=1, batch=1):
+def cpu_baseline_sample(steps=8, warmup=1, batch=1):
     threads = os.cpu_count() or 1
     step = _oracle_encoder(threads)
     c0, _, d0 = stage_specs()[0]
@@ -354,7 +358,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 8)), max(1, min(args.warmup, 1))
     cpu = cpu_baseline_sample(steps=steps, warmup=warmup, batch=1)
     line = {
         "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus,
@@ -378,6 +382,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=4, help="per-GPU batch (BASELINE config[1]: 4)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cuda-profiler-range", action="store_true",
+                    help="bracket the HBM-resident timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -188,8 +188,11 @@ def test_pair_with_merge_and_checkpoint():
             assert rel_linf(y, torch.from_numpy(d[f"{tag}.out"])) < RTOL_F32
             y.square().sum().backward()
             outs.append((y.detach(), x.grad.clone(), p0.grad.clone()))
-        for a, b in zip(*outs):   # activation checkpointing (swin_block.py:257-260) must not change anything
-            assert torch.equal(a, b)
+        # activation checkpointing (swin_block.py:257-260) must not change anything; forward is bit-identical,
+        # gradients agree to fp32 atomics ordering (prompt / bias-table grads are atomically accumulated)
+        assert torch.equal(outs[0][0], outs[1][0])
+        for a, b in zip(outs[0][1:], outs[1][1:]):
+            assert rel_linf(a, b) < 1e-5
 
 
 def test_full_size_attention_properties():

@@ -123,6 +123,37 @@ def test_attention_kernel_vs_oracle(case, dtype, rtol):
             assert rel_linf(t.grad, g) < rtol, n
 
 
+TC_CASES = [  # B, P, ws, C, heads, I, masked      (tcgen05 kernel: N = 256, bf16)
+    (1, 2, (8, 8, 4), 48, 4, 64, True), (2, 3, (8, 8, 4), 48, 4, 64, False), (1, 2, (8, 8, 4), 96, 8, 64, True),
+    (1, 1, (8, 8, 4), 96, 4, 64, True), (1, 1, (8, 8, 4), 192, 4, 64, True), (1, 2, (8, 8, 4), 48, 4, 0, True),
+    (1, 1, (8, 8, 4), 192, 16, 64, True), (1, 2, (8, 8, 4), 12, 4, 64, True), (1, 2, (4, 8, 8), 48, 4, 32, True),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_attention_tcgen05_vs_oracle(case):
+    """bf16 tcgen05/TMEM forward kernel (impl=2) against the fp64 oracle on bf16-rounded inputs."""
+    B, P, ws, C, heads, I, masked = case
+    ten, ids, go = _attn_inputs(B, P, ws, C, heads, I, masked, seed=5)
+    scale = (C // heads) ** -0.5
+    dtype = torch.bfloat16
+    ten_r = [None if t is None else (t.to(dtype).double() if i < 5 else t.float().double()) for i, t in enumerate(ten)]
+    ref_out, ref_grads = _oracle_attn(ten_r, ids, go.to(dtype).double(), heads, ws, scale)
+    dev = [None if t is None else (t.to(DEV, dtype) if i < 5 else t.to(DEV, torch.float32)).requires_grad_(True)
+           for i, t in enumerate(ten)]
+    ids_d = None if ids is None else ids.to(DEV)
+    out = PF.prompted_window_attention(*dev, ids_d, heads, ws, scale, PF.IMPL_TC)
+    assert rel_linf(out, ref_out) < RTOL_BF16
+    # fp32-math kernel on the same inputs must agree even closer (same bf16 I/O rounding)
+    out32 = PF.prompted_window_attention(*[t.detach() if t is not None else None for t in dev], ids_d, heads, ws, scale,
+                                         PF.IMPL_F32)
+    assert rel_linf(out, out32) < RTOL_BF16
+    out.backward(go.to(DEV, dtype))
+    for n, t, g in zip(["q", "k", "v", "kp", "vp", "th", "tw", "td", "tok"], dev, ref_grads):
+        if t is not None:
+            assert rel_linf(t.grad, g) < RTOL_BF16, n
+
+
 def _make_block(meta, sd, dtype=torch.float32):
     blk = pwa_b200.SwinTransformerBlock(hidden_channels=meta["C"], window_size=meta["ws"],
                                         pos_bias_embed_dim=meta["E"], num_heads=meta["heads"], max_prompts=1,

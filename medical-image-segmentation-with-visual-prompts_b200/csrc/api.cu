@@ -82,6 +82,11 @@ extern "C" int pwa_attn_bwd(const void* q, const void* k, const void* v, const v
     PWA_CUDA_OK(cudaMemsetAsync(dkp, 0, (size_t)p.B * p.I * p.C * 4, st));
     PWA_CUDA_OK(cudaMemsetAsync(dvp, 0, (size_t)p.B * p.I * p.C * 4, st));
   }
-  (void)impl;  // only the fp32-math backward exists so far
+  const bool tc_ok = attn_tc_bwd_supported(p, dtype);
+  if (impl == 2 && !tc_ok) {
+    set_error("pwa_attn_bwd: tcgen05 kernel does not support this shape/dtype");
+    return PWA_ERR_UNSUPPORTED;
+  }
+  if (impl == 2 || (impl == 0 && tc_ok)) return attn_tc_backward(p, st);
   return attn_f32_backward(p, dtype, st);
 }

@@ -369,7 +369,7 @@ bool attn_tc_supported(const AttnParams& p, int dtype) {
   if (dtype != PWA_BF16) return false;
   if (p.N != kN) return false;                                   // two 128-row tiles / two 128-key content blocks
   if (p.wd > 4 || p.wh + p.ww > 16) return false;                // one-hot bias columns must fit the layout
-  if (p.I % 16 != 0 || p.I > 128) return false;                  // prompt block = one MMA of N = I
+  if (p.I % 32 != 0 || p.I > 128) return false;                  // prompt block = one MMA of N = I, read in 32-column chunks
   const int dh = p.C / p.heads;
   if (!(dh == 12 || dh == 24 || dh == 48 || dh == 6 || dh == 3)) return false;
   const TcSmem L = tc_layout((dh + 4 + 15) / 16, (dh + 15) / 16 * 16, kN + p.I);

@@ -127,7 +127,7 @@ TC_CASES = [  # B, P, ws, C, heads, I, masked      (tcgen05 kernel: N = 256, bf1
     (1, 2, (8, 8, 4), 48, 4, 64, True), (2, 3, (8, 8, 4), 48, 4, 64, False), (1, 2, (8, 8, 4), 96, 8, 64, True),
     (1, 1, (8, 8, 4), 96, 4, 64, True), (1, 1, (8, 8, 4), 192, 4, 64, True), (1, 2, (8, 8, 4), 48, 4, 0, True),
     (1, 1, (8, 8, 4), 192, 16, 64, True), (1, 2, (8, 8, 4), 12, 4, 64, True), (1, 2, (8, 8, 4), 48, 4, 32, True),
-    (2, 5, (8, 8, 4), 24, 4, 16, False),
+    (2, 5, (8, 8, 4), 24, 4, 32, False),
 ]
 
 

@@ -249,9 +249,194 @@ __global__ void __launch_bounds__(256) reverse_fast_kernel(const uint32_t* __res
 }
 
 // ---------------------------------------------------------------------------------------------
+// vector kernels: same slab decomposition and smem tile as the word kernels above, but the x side moves
+// 16-byte vectors (8 bf16 / 4 fp32 along D) and all index arithmetic is hoisted to once per warp-iteration.
+// Lane mapping on the x side: bf16: lane = (channel pair & 7) + 8 * (d vector & 3)   -> 8 pairs x 64 B runs
+//                             fp32: lane = (channel & 3)      + 4 * (d vector & 7)   -> 4 channels x 128 B runs
+// which makes the transposing smem accesses bank-conflict free for an odd word pitch.
+// Token side: a warp owns a (window p3, w') pair = wd consecutive tokens; lanes run over their channel words.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTokK = 8;  // max 32-word chunks per (p3, w') token run
+
+template <int EB>
+struct VecCfg {
+  static constexpr int EPV = 16 / EB;            // elements (d positions) per 16-byte vector
+  static constexpr int CL = EB == 2 ? 8 : 4;     // channel-word lanes
+  static constexpr int DL = 32 / CL;             // d-vector lanes
+  static constexpr int CPW = 4 / EB;             // channels per word
+};
+
+struct TokMap {
+  int soff[kTokK];
+  int goff[kTokK];
+  int nk;
+};
+
+__device__ __forceinline__ TokMap make_tok_map(const PartParams& p, int CW, int lane, int tok_w) {
+  TokMap m;
+  const int total = p.wd * CW;
+  m.nk = (total + 31) / 32;
+#pragma unroll
+  for (int k = 0; k < kTokK; ++k) {
+    const int idx = lane + 32 * k;
+    const int t3 = idx / CW, cw = idx - t3 * CW;
+    const bool ok = idx < total;
+    m.soff[k] = ok ? t3 * p.P3 * p.pitch + cw : -1;
+    m.goff[k] = t3 * tok_w + cw;
+  }
+  return m;
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) partition_vec_kernel(const uint32_t* __restrict__ x, uint32_t* __restrict__ tok,
+                                                            PartParams p) {
+  using V = VecCfg<EB>;
+  extern __shared__ uint32_t smem[];
+  const Slab<EB> s(p);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int CW = p.CT / V::CPW;
+  const int rows = p.ww * p.Dp;
+  if (p.padded) {
+    for (int i = tid; i < rows * p.pitch; i += 256) smem[i] = 0u;
+    __syncthreads();
+  }
+  // ---- phase 1: x lines -> smem ----
+  if (s.h >= 0 && s.h < p.H) {
+    const int DV = p.D / V::EPV;
+    const int n_cg = (CW + V::CL - 1) / V::CL, n_dg = (DV + V::DL - 1) / V::DL;
+    const int items = n_cg * p.ww * n_dg;
+    const size_t plane = (size_t)p.H * p.W * p.D;
+    const uint32_t* xb = x + (((size_t)s.b * p.C + (size_t)s.chunk * p.CT) * plane + (size_t)s.h * p.W * p.D) / V::CPW;
+    const size_t plane_w = plane / V::CPW;                  // words per channel plane
+    const int cl = lane % V::CL, dl = lane / V::CL;
+    for (int it = warp; it < items; it += 8) {
+      const int dg = it % n_dg;
+      const int r = it / n_dg;
+      const int t2 = r % p.ww, cg = r / p.ww;
+      const int w = (t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      const int cw = cg * V::CL + cl, dvec = dg * V::DL + dl;
+      if (w < 0 || w >= p.W || cw >= CW || dvec >= DV) continue;
+      int rr = roll_fwd(dvec * V::EPV, p.lod, p.sd, p.Dp);
+      uint32_t* srow = smem + (t2 * p.Dp) * p.pitch + cw;
+      if (EB == 4) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(xb + (size_t)cw * plane_w + (size_t)w * p.D + dvec * 4));
+        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          srow[rr * p.pitch] = vv[j];
+          rr = (rr + 1 == p.Dp) ? 0 : rr + 1;
+        }
+      } else {
+        const uint32_t* g0 = xb + (size_t)(2 * cw) * plane_w + ((size_t)w * p.D + dvec * 8) / 2;
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(g0));
+        const uint4 b = __ldg(reinterpret_cast<const uint4*>(g0 + plane_w));
+        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          srow[rr * p.pitch] = __byte_perm(av[j], bv[j], 0x5410);
+          rr = (rr + 1 == p.Dp) ? 0 : rr + 1;
+          srow[rr * p.pitch] = __byte_perm(av[j], bv[j], 0x7632);
+          rr = (rr + 1 == p.Dp) ? 0 : rr + 1;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: smem -> tokens ----
+  {
+    const int tok_w = p.C / V::CPW;
+    const TokMap m = make_tok_map(p, CW, lane, tok_w);
+    const size_t win0 = ((size_t)s.b * p.P + ((size_t)s.p1 * p.P2 + s.p2) * p.P3);
+    const size_t row0 = (size_t)s.t1 * p.ww * p.wd;
+    const size_t cw0 = (size_t)s.chunk * CW;
+    const int items = p.P3 * p.ww;
+    for (int it = warp; it < items; it += 8) {
+      const int t2 = it % p.ww, p3 = it / p.ww;
+      const uint32_t* sb = smem + (t2 * p.Dp + p3) * p.pitch;
+      uint32_t* gb = tok + ((win0 + p3) * p.N + row0 + (size_t)t2 * p.wd) * tok_w + cw0;
+#pragma unroll
+      for (int k = 0; k < kTokK; ++k)
+        if (k < m.nk && m.soff[k] >= 0) gb[m.goff[k]] = sb[m.soff[k]];
+    }
+  }
+}
+
+template <int EB>
+__global__ void __launch_bounds__(256) reverse_vec_kernel(const uint32_t* __restrict__ tok, uint32_t* __restrict__ x,
+                                                          PartParams p) {
+  using V = VecCfg<EB>;
+  extern __shared__ uint32_t smem[];
+  const Slab<EB> s(p);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int CW = p.CT / V::CPW;
+  if (!(s.h >= 0 && s.h < p.H)) return;
+  // ---- phase 1: tokens -> smem ----
+  {
+    const int tok_w = p.C / V::CPW;
+    const TokMap m = make_tok_map(p, CW, lane, tok_w);
+    const size_t win0 = ((size_t)s.b * p.P + ((size_t)s.p1 * p.P2 + s.p2) * p.P3);
+    const size_t row0 = (size_t)s.t1 * p.ww * p.wd;
+    const size_t cw0 = (size_t)s.chunk * CW;
+    const int items = p.P3 * p.ww;
+    for (int it = warp; it < items; it += 8) {
+      const int t2 = it % p.ww, p3 = it / p.ww;
+      uint32_t* sb = smem + (t2 * p.Dp + p3) * p.pitch;
+      const uint32_t* gb = tok + ((win0 + p3) * p.N + row0 + (size_t)t2 * p.wd) * tok_w + cw0;
+#pragma unroll
+      for (int k = 0; k < kTokK; ++k)
+        if (k < m.nk && m.soff[k] >= 0) sb[m.soff[k]] = __ldg(gb + m.goff[k]);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: smem -> x lines ----
+  {
+    const int DV = p.D / V::EPV;
+    const int n_cg = (CW + V::CL - 1) / V::CL, n_dg = (DV + V::DL - 1) / V::DL;
+    const int items = n_cg * p.ww * n_dg;
+    const size_t plane = (size_t)p.H * p.W * p.D;
+    uint32_t* xb = x + (((size_t)s.b * p.C + (size_t)s.chunk * p.CT) * plane + (size_t)s.h * p.W * p.D) / V::CPW;
+    const size_t plane_w = plane / V::CPW;
+    const int cl = lane % V::CL, dl = lane / V::CL;
+    for (int it = warp; it < items; it += 8) {
+      const int dg = it % n_dg;
+      const int r = it / n_dg;
+      const int t2 = r % p.ww, cg = r / p.ww;
+      const int w = (t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      const int cw = cg * V::CL + cl, dvec = dg * V::DL + dl;
+      if (w < 0 || w >= p.W || cw >= CW || dvec >= DV) continue;
+      int rr = roll_fwd(dvec * V::EPV, p.lod, p.sd, p.Dp);
+      const uint32_t* srow = smem + (t2 * p.Dp) * p.pitch + cw;
+      if (EB == 4) {
+        uint32_t vv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          vv[j] = srow[rr * p.pitch];
+          rr = (rr + 1 == p.Dp) ? 0 : rr + 1;
+        }
+        *reinterpret_cast<uint4*>(xb + (size_t)cw * plane_w + (size_t)w * p.D + dvec * 4) = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+      } else {
+        uint32_t av[4], bv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t lo = srow[rr * p.pitch];
+          rr = (rr + 1 == p.Dp) ? 0 : rr + 1;
+          const uint32_t hi = srow[rr * p.pitch];
+          rr = (rr + 1 == p.Dp) ? 0 : rr + 1;
+          av[j] = __byte_perm(lo, hi, 0x5410);
+          bv[j] = __byte_perm(lo, hi, 0x7632);
+        }
+        uint32_t* g0 = xb + (size_t)(2 * cw) * plane_w + ((size_t)w * p.D + dvec * 8) / 2;
+        *reinterpret_cast<uint4*>(g0) = make_uint4(av[0], av[1], av[2], av[3]);
+        *reinterpret_cast<uint4*>(g0 + plane_w) = make_uint4(bv[0], bv[1], bv[2], bv[3]);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int fill_params(PartParams& p, int B, int C, const pwa_geom* g, int use_crop_lo, int eb, bool* fast) {
+static int fill_params(PartParams& p, int B, int C, const pwa_geom* g, int use_crop_lo, int eb, bool* fast, bool* vec) {
   p.B = B; p.C = C;
   p.H = g->dims[0]; p.W = g->dims[1]; p.D = g->dims[2];
   p.Hp = g->sp[0]; p.Wp = g->sp[1]; p.Dp = g->sp[2];
@@ -285,7 +470,33 @@ static int fill_params(PartParams& p, int B, int C, const pwa_geom* g, int use_c
     p.div_ww = FastDiv(p.ww);
   }
   *fast = ok;
+  // vector path: whole 16-byte vectors along D, token runs that fit the per-lane offset table
+  *vec = ok && ((p.D * eb) % 16 == 0) && (p.wd * (p.CT / epw) <= 32 * kTokK) &&
+         ((size_t)p.H * p.W * p.D * eb) % 16 == 0;
   return 0;
+}
+
+template <int EB>
+static int launch_vec(bool is_partition, const void* src, void* dst, const PartParams& p, cudaStream_t st) {
+  size_t smem = (size_t)p.ww * p.Dp * p.pitch * 4;
+  dim3 grid((unsigned)((size_t)p.B * p.Hp * p.P2 * p.nchunk));
+  if (is_partition) {
+    static bool attr_done = false;  // benign race: idempotent
+    if (!attr_done) {
+      PWA_CUDA_OK(cudaFuncSetAttribute(partition_vec_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    partition_vec_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
+  } else {
+    static bool attr_done = false;
+    if (!attr_done) {
+      PWA_CUDA_OK(cudaFuncSetAttribute(reverse_vec_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done = true;
+    }
+    reverse_vec_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
+  }
+  PWA_CUDA_OK(cudaGetLastError());
+  return PWA_OK;
 }
 
 template <int EB>
@@ -332,12 +543,15 @@ static int run(bool is_partition, const void* src, void* dst, int B, int C, cons
   PWA_CHECK_ARG(dtype == PWA_F32 || dtype == PWA_BF16, "pwa_partition/reverse: bad dtype %d", dtype);
   const int eb = dtype == PWA_F32 ? 4 : 2;
   PartParams p;
-  bool fast = false;
-  fill_params(p, B, C, g, use_crop_lo, eb, &fast);
-  // `use_crop_lo & 2` forces the generic kernel (used by the tests to cross-check the fast path)
-  if (use_crop_lo & 2) fast = false;
-  if (((uintptr_t)src | (uintptr_t)dst) & 3) fast = false;  // fast path moves aligned 32-bit words
+  bool fast = false, vec = false;
+  fill_params(p, B, C, g, use_crop_lo, eb, &fast, &vec);
+  // `use_crop_lo & 2` forces the generic kernel, `& 4` the word kernel (tests cross-check the three paths)
+  if (use_crop_lo & 2) fast = vec = false;
+  if (use_crop_lo & 4) vec = false;
+  if (((uintptr_t)src | (uintptr_t)dst) & 3) fast = false;   // staged paths move aligned 32-bit words
+  if (((uintptr_t)src | (uintptr_t)dst) & 15) vec = false;   // ... or aligned 16-byte vectors
   cudaStream_t st = (cudaStream_t)stream;
+  if (fast && vec) return eb == 4 ? launch_vec<4>(is_partition, src, dst, p, st) : launch_vec<2>(is_partition, src, dst, p, st);
   if (fast) return eb == 4 ? launch_fast<4>(is_partition, src, dst, p, st) : launch_fast<2>(is_partition, src, dst, p, st);
   return eb == 4 ? launch_generic<uint32_t>(is_partition, src, dst, p, st)
                  : launch_generic<uint16_t>(is_partition, src, dst, p, st);

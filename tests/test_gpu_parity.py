@@ -17,6 +17,7 @@ RTOL_F32 = 1e-4
 RTOL_BF16 = 2e-2
 
 GEOMS = [
+    ((16, 16, 16), (8, 8, 4), (4, 4, 2)), ((8, 8, 24), (4, 4, 2), (2, 2, 1)), ((12, 12, 8), (8, 8, 4), (4, 4, 2)),
     ((8, 8, 4), (4, 4, 2), (2, 2, 1)), ((6, 6, 6), (4, 4, 2), (2, 2, 1)), ((6, 8, 4), (4, 4, 2), (2, 2, 1)),
     ((8, 8, 2), (4, 4, 2), (2, 2, 1)), ((5, 9, 3), (4, 4, 2), (2, 2, 1)), ((16, 16, 8), (8, 8, 4), (4, 4, 2)),
     ((12, 12, 24), (8, 8, 4), (4, 4, 2)), ((24, 24, 24), (8, 8, 4), (0, 0, 0)), ((24, 24, 24), (8, 8, 4), (4, 4, 2)),
@@ -25,7 +26,7 @@ GEOMS = [
 
 @pytest.mark.parametrize("dims,ws,shift_cfg", GEOMS)
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("C", [12, 48, 7])
+@pytest.mark.parametrize("C", [12, 48, 7, 96])
 def test_partition_reverse_bit_exact(dims, ws, shift_cfg, dtype, C):
     g = pwa_b200.get_geometry(dims, ws, shift_cfg)
     pads, shift = R.pad_amounts(dims, ws), R.effective_shift(dims, ws, shift_cfg)
@@ -36,12 +37,14 @@ def test_partition_reverse_bit_exact(dims, ws, shift_cfg, dtype, C):
     got = PF._partition_raw(xd, g, 0)
     assert torch.equal(got.cpu(), exp)
     assert torch.equal(PF._partition_raw(xd, g, 0, force_generic=True).cpu(), exp)
+    assert torch.equal(PF._partition_raw(xd, g, 0, force_word=True).cpu(), exp)
     # output side: window reverse + roll back + crop (crop offsets), and the two adjoints
     t = torch.randn(2, g.P, g.N, C, generator=gen).to(dtype)
     exp_r = R.reverse_tokens(t.float(), dims, ws, shift, pads).to(dtype)
     td = t.to(DEV)
     assert torch.equal(PF._reverse_raw(td, g, 1).cpu(), exp_r)
     assert torch.equal(PF._reverse_raw(td, g, 1, force_generic=True).cpu(), exp_r)
+    assert torch.equal(PF._reverse_raw(td, g, 1, force_word=True).cpu(), exp_r)
     idx0 = torch.from_numpy(R.gather_index(dims, ws, shift, pads)).reshape(-1)
     adj = torch.zeros(2, C, dims[0] * dims[1] * dims[2] + 1, dtype=dtype)
     adj[:, :, idx0] = t.permute(0, 3, 1, 2).reshape(2, C, -1)       # unique targets except the -1 slot
@@ -61,9 +64,11 @@ def test_partition_full_size_round_trip(dims, C, B, dtype):
         x = torch.randn(B, C, *dims, device=DEV).to(dtype)
         tok = PF._partition_raw(x, g, 0)
         assert torch.equal(tok, PF._partition_raw(x, g, 0, force_generic=True))
+        assert torch.equal(tok, PF._partition_raw(x, g, 0, force_word=True))
         back = PF._reverse_raw(tok, g, 0)
         assert torch.equal(back, x)
         assert torch.equal(back, PF._reverse_raw(tok, g, 0, force_generic=True))
+        assert torch.equal(back, PF._reverse_raw(tok, g, 0, force_word=True))
         # checksum of checksums: a permutation (+ zero padding) preserves the multiset of values
         assert torch.equal(tok.float().sum(dim=(1, 2)).sum(), tok.float().sum(dim=(1, 2)).sum())
         assert tok.count_nonzero() == x.count_nonzero()

@@ -122,6 +122,21 @@ int pwa_attn_bwd(const void* q, const void* k, const void* v, const void* kp, co
                  float* dth, float* dtw, float* dtd, float* dtok, float* delta,
                  const pwa_attn_shape* s, int dtype, int impl, void* stream);
 
+/* ---- LayerNorm over the channel axis of window tokens, fused with the surrounding residual adds ----- */
+
+/* s = x (+ res) ; y = LayerNorm(s) * gamma + beta over the last axis (C, C % 4 == 0, C <= 1024), rows x C
+ * row-major.  Replaces nn.LayerNorm(eps=1e-6) at swin_block.py:216 (attn_norm) and :227 (mlp_norm) together
+ * with the residual add of :222.  res / sum_out may be NULL (plain LayerNorm).  gamma, beta fp32.
+ * mean, rstd: fp32 [rows], saved for the backward. */
+int pwa_ln_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* sum_out, void* y,
+               float* mean, float* rstd, int64_t rows, int C, float eps, int dtype, void* stream);
+
+/* dx = LayerNorm-backward(dy; x, gamma, mean, rstd) (+ dres) ; dgamma = sum_rows dy*xhat ; dbeta = sum_rows dy.
+ * x is the tensor that was normalised (the sum when a residual was fused).  dres may be NULL.
+ * dgamma/dbeta fp32 [C], zeroed by this call. */
+int pwa_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+               const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int dtype, void* stream);
+
 /* 1 iff the bf16 tcgen05 kernel supports this shape (else impl=0 falls back to the fp32-math kernel). */
 int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype);
 

@@ -53,6 +53,10 @@ def _load():
     lib.pwa_attn_tc_supported.argtypes = [sp, i32]
     lib.pwa_attn_fwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, sp, i32, i32, vp]
     lib.pwa_attn_bwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, vp] + [vp] * 3 + [f32p] * 7 + [sp, i32, i32, vp]
+    i64, f32 = C.c_int64, C.c_float
+    lib.pwa_ln_fwd.argtypes = [vp, vp, f32p, f32p, vp, vp, f32p, f32p, i64, i32, f32, i32, vp]
+    lib.pwa_ln_bwd.argtypes = [vp, vp, f32p, f32p, f32p, vp, vp, f32p, f32p, i64, i32, i32, vp]
+    lib.pwa_ln_fwd.restype = lib.pwa_ln_bwd.restype = i32
     for name in ("pwa_geometry", "pwa_region_ids", "pwa_index_map", "pwa_partition", "pwa_reverse",
                  "pwa_attn_tc_supported", "pwa_attn_fwd", "pwa_attn_bwd"):
         getattr(lib, name).restype = i32
@@ -62,7 +66,8 @@ def _load():
 lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
-                    "pwa_partition", "pwa_reverse", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported")
+                    "pwa_partition", "pwa_reverse", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
+                    "pwa_ln_fwd", "pwa_ln_bwd")
 
 
 def check(rc: int, what: str):

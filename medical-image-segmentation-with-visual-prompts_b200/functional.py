@@ -207,3 +207,72 @@ def prompted_window_attention(q, k, v, kp, vp, th, tw, td, tok, ids, heads: int,
     if q.shape[-1] % heads != 0:
         raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
     return _WindowAttention.apply(q, k, v, kp, vp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl)
+
+
+# ------------------------------------------------------------------------------------------------
+# LayerNorm over channels (+ fused residual add)
+# ------------------------------------------------------------------------------------------------
+class _AddLayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        x = x.contiguous()
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        s = None
+        if res is not None:
+            res = res.contiguous()
+            s = torch.empty_like(x)
+        nbytes = (2 if res is None else 4) * x.numel() * x.element_size()
+        with torch.cuda.device(x.device), _timed("ln_fwd", 1, float(nbytes), x):
+            rc = _lib.lib.pwa_ln_fwd(_ptr(x), _ptr(res), _ptr(g32), _ptr(b32), _ptr(s), _ptr(y), _ptr(mean), _ptr(rstd),
+                                     rows, Cc, float(eps), _dtype_code(x), _stream(x))
+        _lib.check(rc, "pwa_ln_fwd")
+        normed = x if res is None else s
+        ctx.save_for_backward(normed, g32, mean, rstd)
+        ctx.has_res = res is not None
+        ctx.param_dtypes = (gamma.dtype, beta.dtype)
+        if res is None:
+            return y
+        return s, y
+
+    @staticmethod
+    def backward(ctx, *grads):
+        normed, g32, mean, rstd = ctx.saved_tensors
+        if ctx.has_res:
+            ds, dy = grads
+        else:
+            (dy,), ds = grads, None
+        Cc = normed.shape[-1]
+        rows = normed.numel() // Cc
+        dy = dy.contiguous() if dy is not None else torch.zeros_like(normed)
+        ds = ds.contiguous() if ds is not None else None
+        dx = torch.empty_like(normed)
+        dg = torch.empty(Cc, dtype=torch.float32, device=normed.device)
+        db = torch.empty(Cc, dtype=torch.float32, device=normed.device)
+        nbytes = (3 if ds is None else 4) * normed.numel() * normed.element_size()
+        with torch.cuda.device(normed.device), _timed("ln_bwd", 1, float(nbytes), normed):
+            rc = _lib.lib.pwa_ln_bwd(_ptr(dy), _ptr(normed), _ptr(g32), _ptr(mean), _ptr(rstd), _ptr(ds), _ptr(dx), _ptr(dg),
+                                     _ptr(db), rows, Cc, _dtype_code(normed), _stream(normed))
+        _lib.check(rc, "pwa_ln_bwd")
+        gd, bd = ctx.param_dtypes
+        return dx, (dx if ctx.has_res else None), dg.to(gd), db.to(bd), None
+
+
+def layer_norm(x, gamma, beta, eps: float = 1e-6):
+    """LayerNorm over the last axis on the pwa kernel (C % 4 == 0, C <= 1024)."""
+    _require_cuda(x, gamma, beta)
+    return _AddLayerNorm.apply(x, None, gamma, beta, eps)
+
+
+def add_layer_norm(x, res, gamma, beta, eps: float = 1e-6):
+    """(s, y) with s = x + res and y = LayerNorm(s): the residual add of swin_block.py:222 fused into mlp_norm."""
+    _require_cuda(x, res, gamma, beta)
+    return _AddLayerNorm.apply(x, res, gamma, beta, eps)
+
+
+def layer_norm_supported(C: int) -> bool:
+    return C % 4 == 0 and C <= 1024

@@ -30,7 +30,11 @@ class PatchMerging(nn.Module):
             parts = [x[:, :, a::2, b::2, :] for a, b in _OFFS2]
         t = torch.cat(parts, dim=1).permute(0, 2, 3, 4, 1)             # [B,h/2,w/2,d',kC] channels last
         dt = t.dtype
-        t = F.layer_norm(t, self.norm.normalized_shape, self.norm.weight.to(dt), self.norm.bias.to(dt), self.norm.eps)
+        from ... import functional as PF
+        if t.is_cuda and PF.layer_norm_supported(t.shape[-1]):
+            t = PF.layer_norm(t.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps)
+        else:
+            t = F.layer_norm(t, self.norm.normalized_shape, self.norm.weight.to(dt), self.norm.bias.to(dt), self.norm.eps)
         t = F.linear(t, self.reduction.weight.to(dt))
         return t.permute(0, 4, 1, 2, 3).contiguous()
 

@@ -116,13 +116,22 @@ class SwinTransformerBlock(nn.Module):
         with torch.autocast('cuda', enabled=False):
             xw = PF.partition_tokens(x.to(cdt), geom)                       # [B,P,N,C] = shortcut
             c = xw.shape[-1]
-            nw, nb = self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt)
-            tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)
-            prompts = F.layer_norm(p.to(cdt), (c,), nw, nb, 1e-6) if p is not None else None
-            y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                          prompts=prompts)
-            y = y + xw
-            z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
+            if PF.layer_norm_supported(c):
+                # pwa LayerNorm kernels (csrc/ln.cu); the `+ shortcut` of :222 is fused into mlp_norm
+                tokens = PF.layer_norm(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
+                prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6) \
+                    if p is not None else None
+                a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
+                              prompts=prompts)
+                y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6)
+            else:
+                nw, nb = self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt)
+                tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)
+                prompts = F.layer_norm(p.to(cdt), (c,), nw, nb, 1e-6) if p is not None else None
+                y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
+                              prompts=prompts)
+                y = y + xw
+                z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
             y = y + F.linear(z, self.mlp.weight.to(cdt), self.mlp.bias.to(cdt))
             out = PF.reverse_tokens(y, geom)                                # [B,C,H,W,D]
         return out.to(in_dtype)

@@ -262,3 +262,42 @@ def test_block_full_size_runs_and_matches_oracle_sample():
     y16 = blk(x.bfloat16(), p.bfloat16())
     assert y32.shape == x.shape
     assert rel_linf(y16, y32) < RTOL_BF16
+
+
+@pytest.mark.parametrize("C", [12, 48, 96, 192, 384, 768])
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-5), (torch.bfloat16, RTOL_BF16)])
+@pytest.mark.parametrize("with_res", [False, True])
+def test_layer_norm_kernels(C, dtype, rtol, with_res):
+    """pwa LayerNorm (+ fused residual add) forward/backward against torch in float64."""
+    gen = torch.Generator().manual_seed(C)
+    rows = 1000 + C                                        # not a multiple of the rows-per-CTA tile
+    x = torch.randn(rows, C, generator=gen).to(dtype)
+    res = torch.randn(rows, C, generator=gen).to(dtype) if with_res else None
+    gamma = 1 + 0.3 * torch.randn(C, generator=gen)
+    beta = 0.2 * torch.randn(C, generator=gen)
+    go_y = torch.randn(rows, C, generator=gen).to(dtype)
+    go_s = torch.randn(rows, C, generator=gen).to(dtype)
+    x64 = x.double().requires_grad_(True)
+    r64 = res.double().requires_grad_(True) if with_res else None
+    g64, b64 = gamma.double().requires_grad_(True), beta.double().requires_grad_(True)
+    s64 = x64 + r64 if with_res else x64
+    if with_res and dtype == torch.bfloat16:
+        s64 = s64 + (s64.detach().to(dtype).double() - s64.detach())      # the kernel normalises the STORED bf16 sum
+    y64 = torch.nn.functional.layer_norm(s64, (C,), g64, b64, 1e-6)
+    loss = (y64 * go_y.double()).sum() + ((s64 * go_s.double()).sum() if with_res else 0)
+    loss.backward()
+    xd = x.to(DEV).requires_grad_(True)
+    rd = res.to(DEV).requires_grad_(True) if with_res else None
+    gd, bd = gamma.to(DEV).requires_grad_(True), beta.to(DEV).requires_grad_(True)
+    if with_res:
+        s, y = PF.add_layer_norm(xd, rd, gd, bd, 1e-6)
+        assert rel_linf(s, s64) < rtol
+        (y.float() * go_y.to(DEV).float()).sum().add((s.float() * go_s.to(DEV).float()).sum()).backward()
+        assert rel_linf(rd.grad, r64.grad) < rtol
+    else:
+        y = PF.layer_norm(xd, gd, bd, 1e-6)
+        y.backward(go_y.to(DEV))
+    assert rel_linf(y, y64) < rtol
+    assert rel_linf(xd.grad, x64.grad) < rtol
+    assert rel_linf(gd.grad, g64.grad) < rtol
+    assert rel_linf(bd.grad, b64.grad) < rtol

@@ -86,6 +86,11 @@ int pwa_partition(const void* x, void* tokens, int B, int C, const pwa_geom* g, 
 int pwa_reverse(const void* tokens, void* x, int B, int C, const pwa_geom* g, int use_crop_lo,
                 int dtype, void* stream);
 
+/* pwa_reverse of (tokens_a + tokens_b): fuses the last residual add of the block, `x + mlp(mlp_norm(x))`
+ * (swin_block.py:227), into the window reverse.  The sum is formed in fp32 and rounded once to `dtype`. */
+int pwa_reverse_add(const void* tokens_a, const void* tokens_b, void* x, int B, int C, const pwa_geom* g,
+                    int use_crop_lo, int dtype, void* stream);
+
 /* ---- (b) fused prompted window attention, forward -------------------------------------------- */
 
 typedef struct pwa_attn_shape {
@@ -94,6 +99,9 @@ typedef struct pwa_attn_shape {
   float scale;                 /* head_dim ** -0.5  (window_attention.py:25)       */
   float p_drop;                /* attention dropout probability (0 in eval)        */
   uint64_t seed, offset;       /* Philox key/counter taken from torch's generator  */
+  int32_t ld_qkv;              /* row stride (elements) of q,k,v and dq,dk,dv; 0 = C.  3*C when q|k|v are the
+                                  column blocks of ONE fused projection output [B][P][N][3C]            */
+  int32_t ld_p;                /* row stride of kp, vp; 0 = C (2*C for a fused [B][I][2C] projection)  */
 } pwa_attn_shape;
 
 /* q,k,v [B][P][N][C]; kp,vp [B][I][C] (NULL when I == 0): keys/values of the prompt tokens,
@@ -121,6 +129,24 @@ int pwa_attn_bwd(const void* q, const void* k, const void* v, const void* kp, co
                  void* dq, void* dk, void* dv, float* dkp, float* dvp,
                  float* dth, float* dtw, float* dtd, float* dtok, float* delta,
                  const pwa_attn_shape* s, int dtype, int impl, void* stream);
+
+/* ---- relative-position bias tables --------------------------------------------------------------- */
+
+/* RelativePE.forward (relative_positional_encoding.py:99-142) in compact form.  enc_a [2*cap_a-1][E],
+ * wc_a [heads][E] (a = h,w,d), enc_tok [I][E], w_tok [heads][E] (NULL when I == 0), all fp32.
+ * Outputs th [heads][ws0][ws0], tw, td, tok [heads][I] INCLUDING the /3 and E^-0.5 factors (:116-123,136-138). */
+int pwa_bias_tables_fwd(const float* enc_h, const float* enc_w, const float* enc_d, const float* wc_h,
+                        const float* wc_w, const float* wc_d, const float* enc_tok, const float* w_tok,
+                        float* th, float* tw, float* td, float* tok, int heads, int E, const int32_t ws[3],
+                        const int32_t cap[3], int I, void* stream);
+
+/* Gradients of the eight parameter tensors from the table gradients produced by pwa_attn_bwd. */
+int pwa_bias_tables_bwd(const float* enc_h, const float* enc_w, const float* enc_d, const float* wc_h,
+                        const float* wc_w, const float* wc_d, const float* enc_tok, const float* w_tok,
+                        const float* dth, const float* dtw, const float* dtd, const float* dtok,
+                        float* denc_h, float* denc_w, float* denc_d, float* dwc_h, float* dwc_w, float* dwc_d,
+                        float* denc_tok, float* dw_tok, int heads, int E, const int32_t ws[3],
+                        const int32_t cap[3], int I, void* stream);
 
 /* ---- LayerNorm over the channel axis of window tokens, fused with the surrounding residual adds ----- */
 

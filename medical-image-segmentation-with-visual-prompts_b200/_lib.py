@@ -26,7 +26,7 @@ class PwaAttnShape(C.Structure):
     _fields_ = [
         ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("I", C.c_int32),
         ("ws", C.c_int32 * 3), ("scale", C.c_float), ("p_drop", C.c_float),
-        ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("seed", C.c_uint64), ("offset", C.c_uint64), ("ld_qkv", C.c_int32), ("ld_p", C.c_int32),
     ]
 
 
@@ -50,6 +50,8 @@ def _load():
     lib.pwa_index_map.argtypes = [gp, i32, vp]
     lib.pwa_partition.argtypes = [vp, vp, i32, i32, gp, i32, i32, vp]
     lib.pwa_reverse.argtypes = [vp, vp, i32, i32, gp, i32, i32, vp]
+    lib.pwa_reverse_add.argtypes = [vp, vp, vp, i32, i32, gp, i32, i32, vp]
+    lib.pwa_reverse_add.restype = i32
     lib.pwa_attn_tc_supported.argtypes = [sp, i32]
     lib.pwa_attn_fwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, sp, i32, i32, vp]
     lib.pwa_attn_bwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, vp] + [vp] * 3 + [f32p] * 7 + [sp, i32, i32, vp]
@@ -57,6 +59,10 @@ def _load():
     lib.pwa_ln_fwd.argtypes = [vp, vp, f32p, f32p, vp, vp, f32p, f32p, i64, i32, f32, i32, vp]
     lib.pwa_ln_bwd.argtypes = [vp, vp, f32p, f32p, f32p, vp, vp, f32p, f32p, i64, i32, i32, vp]
     lib.pwa_ln_fwd.restype = lib.pwa_ln_bwd.restype = i32
+    i32p = C.POINTER(i32)
+    lib.pwa_bias_tables_fwd.argtypes = [f32p] * 8 + [f32p] * 4 + [i32, i32, i32p, i32p, i32, vp]
+    lib.pwa_bias_tables_bwd.argtypes = [f32p] * 8 + [f32p] * 4 + [f32p] * 8 + [i32, i32, i32p, i32p, i32, vp]
+    lib.pwa_bias_tables_fwd.restype = lib.pwa_bias_tables_bwd.restype = i32
     for name in ("pwa_geometry", "pwa_region_ids", "pwa_index_map", "pwa_partition", "pwa_reverse",
                  "pwa_attn_tc_supported", "pwa_attn_fwd", "pwa_attn_bwd"):
         getattr(lib, name).restype = i32
@@ -66,8 +72,8 @@ def _load():
 lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
-                    "pwa_partition", "pwa_reverse", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
-                    "pwa_ln_fwd", "pwa_ln_bwd")
+                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
+                    "pwa_ln_fwd", "pwa_ln_bwd", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 
 def check(rc: int, what: str):

@@ -20,6 +20,9 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
   p.N = p.wh * p.ww * p.wd;
   p.NK = p.N + p.I;
   p.scale = s->scale;
+  p.ldq = s->ld_qkv > 0 ? s->ld_qkv : s->C;
+  p.ldp = s->ld_p > 0 ? s->ld_p : s->C;
+  PWA_CHECK_ARG(p.ldq >= s->C && p.ldp >= s->C, "%s: row strides must be >= C", who);
   return PWA_OK;
 }
 

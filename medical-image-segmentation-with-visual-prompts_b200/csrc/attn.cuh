@@ -14,6 +14,7 @@ struct AttnParams {
   void *dq, *dk, *dv;
   float *dkp, *dvp, *dth, *dtw, *dtd, *dtok, *delta;
   int B, P, C, heads, I, N, NK;
+  int ldq, ldp;      // row strides (elements) of q/k/v (+ dq/dk/dv) and of kp/vp; out/dout/dkp/dvp use C
   int wh, ww, wd;
   float scale;
 };

@@ -51,8 +51,8 @@ __host__ __device__ inline SmemLayout make_layout(int rows_a, int rows_b, int DH
 template <typename T>
 __device__ __forceinline__ const T* kv_row(const AttnParams& p, const void* content, const void* prompt, int b, int win,
                                            int j, int head, int DH) {
-  if (j < p.N) return (const T*)content + (((size_t)b * p.P + win) * p.N + j) * p.C + head * DH;
-  return (const T*)prompt + ((size_t)b * p.I + (j - p.N)) * p.C + head * DH;
+  if (j < p.N) return (const T*)content + (((size_t)b * p.P + win) * p.N + j) * p.ldq + head * DH;
+  return (const T*)prompt + ((size_t)b * p.I + (j - p.N)) * p.ldp + head * DH;
 }
 
 __device__ __forceinline__ void load_tables(const AttnParams& p, const SmemLayout& L, float* sm, int head, int win,
@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
 
   for (int n = tid; n < p.N; n += kThreads) {
     const size_t row = (((size_t)b * p.P + win) * p.N + n);
-    const T* qg = (const T*)p.q + row * p.C + head * DH;
+    const T* qg = (const T*)p.q + row * p.ldq + head * DH;
     float qr[DH], o[DH];
 #pragma unroll
     for (int d = 0; d < DH; ++d) {
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
     const bool live = n < p.N;
     const int nn = live ? n : 0;
     const size_t row = (((size_t)b * p.P + win) * p.N + nn);
-    const T* qg = (const T*)p.q + row * p.C + head * DH;
+    const T* qg = (const T*)p.q + row * p.ldq + head * DH;
     const T* og = (const T*)p.out + row * p.C + head * DH;
     const T* dog = (const T*)p.dout + row * p.C + head * DH;
     float qr[DH], dor[DH], dqr[DH];
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
       if ((tid & 31) == 0) atomicAdd(&sm[L.gtok + i], g);
     }
     if (live) {
-      T* dqg = (T*)p.dq + row * p.C + head * DH;
+      T* dqg = (T*)p.dq + row * p.ldq + head * DH;
 #pragma unroll
       for (int d = 0; d < DH; ++d) dqg[d] = from_f32<T>(dqr[d] * p.scale);
     }
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_f32_kernel(AttnParams p
   for (int i = tid; i < p.N * DH; i += kThreads) {
     int n = i / DH, d = i - n * DH;
     const size_t row = (((size_t)b * p.P + win) * p.N + n);
-    Qs[i] = to_f32(((const T*)p.q)[row * p.C + head * DH + d]) * p.scale;
+    Qs[i] = to_f32(((const T*)p.q)[row * p.ldq + head * DH + d]) * p.scale;
     dOs[i] = to_f32(((const T*)p.dout)[row * p.C + head * DH + d]);
   }
   const size_t stat0 = (((size_t)b * p.P + win) * p.heads + head) * p.N;
@@ -332,8 +332,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_f32_kernel(AttnParams p
     }
     if (content) {
       const size_t row = (((size_t)b * p.P + win) * p.N + j);
-      T* dkg = (T*)p.dk + row * p.C + head * DH;
-      T* dvg = (T*)p.dv + row * p.C + head * DH;
+      T* dkg = (T*)p.dk + row * p.ldq + head * DH;
+      T* dvg = (T*)p.dv + row * p.ldq + head * DH;
 #pragma unroll
       for (int d = 0; d < DH; ++d) {
         dkg[d] = from_f32<T>(dkr[d]);

@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
     __nv_bfloat16 extra[4];
     for (int n = tid; n < kN; n += kRows) {
       __nv_bfloat16 row[DH];
-      load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + n) * p.C + head * DH, row);
+      load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + n) * p.ldq + head * DH, row);
       const int id_ = n % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
     }
     for (int j = tid; j < NKT; j += kRows) {
       const bool content = j < kN;
-      const size_t off = content ? ((size_t)bw * kN + j) * p.C + head * DH : ((size_t)b * p.I + (j - kN)) * p.C + head * DH;
+      const size_t off = content ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
       __nv_bfloat16 row[DH];
       load_row<DH>((const __nv_bfloat16*)(content ? p.k : p.kp) + off, row);
       const int jd = j % p.wd;

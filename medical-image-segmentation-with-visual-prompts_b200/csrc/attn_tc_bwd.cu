@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kThreadsB, (DH <= 12 ? 2 : 1)) attn_bwd_tc_ker
       const int n = tid;                                         // one query row per thread
       const size_t goff = ((size_t)bw * kN + n) * p.C + head * DH;
       __nv_bfloat16 row[DH], orow[DH], extra[4];
-      load_row_b<DH>((const __nv_bfloat16*)p.q + goff, row);
+      load_row_b<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + n) * p.ldq + head * DH, row);
       const int id_ = n % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreadsB, (DH <= 12 ? 2 : 1)) attn_bwd_tc_ker
     }
     for (int j = tid; j < NKT; j += kThreadsB) {
       const bool content = j < kN;
-      const size_t off = content ? ((size_t)bw * kN + j) * p.C + head * DH : ((size_t)b * p.I + (j - kN)) * p.C + head * DH;
+      const size_t off = content ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
       __nv_bfloat16 row[DH], extra[4];
       load_row_b<DH>((const __nv_bfloat16*)(content ? p.k : p.kp) + off, row);
       const int jd = j % p.wd;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(kThreadsB, (DH <= 12 ? 2 : 1)) attn_bwd_tc_ker
         }
         if (key_ok) {
           if (kb < 2) {
-            __nv_bfloat16* g = (__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.C + head * DH;
+            __nv_bfloat16* g = (__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH;
 #pragma unroll
             for (int d = 0; d < DH; ++d) g[d] = __float2bfloat16(dv[d]);
           } else {
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kThreadsB, (DH <= 12 ? 2 : 1)) attn_bwd_tc_ker
         }
         if (key_ok) {
           if (kb < 2) {
-            __nv_bfloat16* g = (__nv_bfloat16*)p.dk + ((size_t)bw * kN + key) * p.C + head * DH;
+            __nv_bfloat16* g = (__nv_bfloat16*)p.dk + ((size_t)bw * kN + key) * p.ldq + head * DH;
 #pragma unroll
             for (int d = 0; d < DH; ++d) g[d] = __float2bfloat16(dk[d] * p.scale);
 #pragma unroll
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(kThreadsB, (DH <= 12 ? 2 : 1)) attn_bwd_tc_ker
 #pragma unroll
         for (int d = 0; d < 16; ++d) dq[c * 16 + d] = __uint_as_float(o[d]);
       }
-      __nv_bfloat16* g = (__nv_bfloat16*)p.dq + ((size_t)bw * kN + wg * 128 + lane_row) * p.C + head * DH;
+      __nv_bfloat16* g = (__nv_bfloat16*)p.dq + ((size_t)bw * kN + wg * 128 + lane_row) * p.ldq + head * DH;
 #pragma unroll
       for (int d = 0; d < DH; ++d) g[d] = __float2bfloat16(dq[d] * p.scale);
     }

@@ -60,7 +60,19 @@ __global__ void partition_generic_kernel(const T* __restrict__ x, T* __restrict_
 }
 
 template <typename T>
-__global__ void reverse_generic_kernel(const T* __restrict__ tok, T* __restrict__ x, PartParams p, size_t total) {
+__device__ __forceinline__ T add_elem(T a, T b);
+template <> __device__ __forceinline__ uint32_t add_elem<uint32_t>(uint32_t a, uint32_t b) {
+  return __float_as_uint(__uint_as_float(a) + __uint_as_float(b));
+}
+template <> __device__ __forceinline__ uint16_t add_elem<uint16_t>(uint16_t a, uint16_t b) {
+  const float fa = __uint_as_float((uint32_t)a << 16), fb = __uint_as_float((uint32_t)b << 16);
+  const __nv_bfloat16 r = __float2bfloat16_rn(fa + fb);
+  return *reinterpret_cast<const uint16_t*>(&r);
+}
+
+template <typename T>
+__global__ void reverse_generic_kernel(const T* __restrict__ tok, const T* __restrict__ tok2, T* __restrict__ x, PartParams p,
+                                       size_t total) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     int d = (int)(i % p.D);
     size_t r = i / p.D;
@@ -79,7 +91,8 @@ __global__ void reverse_generic_kernel(const T* __restrict__ tok, T* __restrict_
     int t3 = rd / p.P3, p3 = rd % p.P3;
     int win = (p1 * p.P2 + p2) * p.P3 + p3;
     int n = (t1 * p.ww + t2) * p.wd + t3;
-    x[i] = tok[(((size_t)b * p.P + win) * p.N + n) * p.C + c];
+    const size_t t = (((size_t)b * p.P + win) * p.N + n) * p.C + c;
+    x[i] = tok2 ? add_elem<T>(tok[t], tok2[t]) : tok[t];
   }
 }
 
@@ -106,6 +119,16 @@ struct Slab {
     h = (a + p.sh) % p.Hp - p.loh;
   }
 };
+
+// word-wise add of two token words: one fp32 or a pair of bf16 (computed in fp32, rounded once: same as torch)
+template <int EB>
+__device__ __forceinline__ uint32_t add_word(uint32_t a, uint32_t b) {
+  if (EB == 4) return __float_as_uint(__uint_as_float(a) + __uint_as_float(b));
+  const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&a), y = *reinterpret_cast<const __nv_bfloat162*>(&b);
+  const float2 fx = __bfloat1622float2(x), fy = __bfloat1622float2(y);
+  const __nv_bfloat162 r = __floats2bfloat162_rn(fx.x + fy.x, fx.y + fy.y);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 __device__ __forceinline__ int roll_fwd(int d, int lo, int s, int S) {  // unpadded -> rolled frame
   int r = d + lo - s;
@@ -186,8 +209,8 @@ __global__ void __launch_bounds__(256) partition_fast_kernel(const uint32_t* __r
 }
 
 template <int EB>
-__global__ void __launch_bounds__(256) reverse_fast_kernel(const uint32_t* __restrict__ tok, uint32_t* __restrict__ x,
-                                                           PartParams p) {
+__global__ void __launch_bounds__(256) reverse_fast_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ tok2,
+                                                           uint32_t* __restrict__ x, PartParams p) {
   extern __shared__ uint32_t smem[];
   const Slab<EB> s(p);
   const int tid = threadIdx.x;
@@ -211,7 +234,9 @@ __global__ void __launch_bounds__(256) reverse_fast_kernel(const uint32_t* __res
       p.div_wwwd.divmod(tk, p3, rem);
       p.div_wd.divmod(rem, t2, t3);
       size_t g = ((win0 + p3) * p.N + row0 + rem) * tok_stride_w + cw0 + cw;
-      smem[(t2 * p.Dp + t3 * p.P3 + p3) * p.pitch + cw] = __ldg(tok + g);
+      uint32_t v = __ldg(tok + g);
+      if (tok2) v = add_word<EB>(v, __ldg(tok2 + g));
+      smem[(t2 * p.Dp + t3 * p.P3 + p3) * p.pitch + cw] = v;
     }
   }
   __syncthreads();
@@ -362,8 +387,8 @@ __global__ void __launch_bounds__(256) partition_vec_kernel(const uint32_t* __re
 }
 
 template <int EB>
-__global__ void __launch_bounds__(256) reverse_vec_kernel(const uint32_t* __restrict__ tok, uint32_t* __restrict__ x,
-                                                          PartParams p) {
+__global__ void __launch_bounds__(256) reverse_vec_kernel(const uint32_t* __restrict__ tok, const uint32_t* __restrict__ tok2,
+                                                          uint32_t* __restrict__ x, PartParams p) {
   using V = VecCfg<EB>;
   extern __shared__ uint32_t smem[];
   const Slab<EB> s(p);
@@ -381,10 +406,15 @@ __global__ void __launch_bounds__(256) reverse_vec_kernel(const uint32_t* __rest
     for (int it = warp; it < items; it += 8) {
       const int t2 = it % p.ww, p3 = it / p.ww;
       uint32_t* sb = smem + (t2 * p.Dp + p3) * p.pitch;
-      const uint32_t* gb = tok + ((win0 + p3) * p.N + row0 + (size_t)t2 * p.wd) * tok_w + cw0;
+      const size_t goff0 = ((win0 + p3) * p.N + row0 + (size_t)t2 * p.wd) * tok_w + cw0;
+      const uint32_t* gb = tok + goff0;
 #pragma unroll
       for (int k = 0; k < kTokK; ++k)
-        if (k < m.nk && m.soff[k] >= 0) sb[m.soff[k]] = __ldg(gb + m.goff[k]);
+        if (k < m.nk && m.soff[k] >= 0) {
+          uint32_t v = __ldg(gb + m.goff[k]);
+          if (tok2) v = add_word<EB>(v, __ldg(tok2 + goff0 + m.goff[k]));
+          sb[m.soff[k]] = v;
+        }
     }
   }
   __syncthreads();
@@ -477,7 +507,7 @@ static int fill_params(PartParams& p, int B, int C, const pwa_geom* g, int use_c
 }
 
 template <int EB>
-static int launch_vec(bool is_partition, const void* src, void* dst, const PartParams& p, cudaStream_t st) {
+static int launch_vec(bool is_partition, const void* src, const void* src2, void* dst, const PartParams& p, cudaStream_t st) {
   size_t smem = (size_t)p.ww * p.Dp * p.pitch * 4;
   dim3 grid((unsigned)((size_t)p.B * p.Hp * p.P2 * p.nchunk));
   if (is_partition) {
@@ -493,14 +523,14 @@ static int launch_vec(bool is_partition, const void* src, void* dst, const PartP
       PWA_CUDA_OK(cudaFuncSetAttribute(reverse_vec_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_done = true;
     }
-    reverse_vec_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
+    reverse_vec_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (const uint32_t*)src2, (uint32_t*)dst, p);
   }
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }
 
 template <int EB>
-static int launch_fast(bool is_partition, const void* src, void* dst, const PartParams& p, cudaStream_t st) {
+static int launch_fast(bool is_partition, const void* src, const void* src2, void* dst, const PartParams& p, cudaStream_t st) {
   size_t smem = (size_t)p.ww * p.Dp * p.pitch * 4;
   dim3 grid((unsigned)((size_t)p.B * p.Hp * p.P2 * p.nchunk));
   if (is_partition) {
@@ -516,14 +546,14 @@ static int launch_fast(bool is_partition, const void* src, void* dst, const Part
       PWA_CUDA_OK(cudaFuncSetAttribute(reverse_fast_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       attr_done = true;
     }
-    reverse_fast_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
+    reverse_fast_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (const uint32_t*)src2, (uint32_t*)dst, p);
   }
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }
 
 template <typename T>
-static int launch_generic(bool is_partition, const void* src, void* dst, const PartParams& p, cudaStream_t st) {
+static int launch_generic(bool is_partition, const void* src, const void* src2, void* dst, const PartParams& p, cudaStream_t st) {
   size_t total = is_partition ? (size_t)p.B * p.P * p.N * p.C : (size_t)p.B * p.C * p.H * p.W * p.D;
   if (total == 0) return PWA_OK;
   unsigned blocks = (unsigned)((total + 255) / 256);
@@ -531,13 +561,13 @@ static int launch_generic(bool is_partition, const void* src, void* dst, const P
   if (is_partition)
     partition_generic_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, (T*)dst, p, total);
   else
-    reverse_generic_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, (T*)dst, p, total);
+    reverse_generic_kernel<T><<<blocks, 256, 0, st>>>((const T*)src, (const T*)src2, (T*)dst, p, total);
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }
 
-static int run(bool is_partition, const void* src, void* dst, int B, int C, const pwa_geom* g, int use_crop_lo,
-               int dtype, void* stream) {
+static int run(bool is_partition, const void* src, const void* src2, void* dst, int B, int C, const pwa_geom* g,
+               int use_crop_lo, int dtype, void* stream) {
   PWA_CHECK_ARG(src && dst && g, "pwa_partition/reverse: null pointer");
   PWA_CHECK_ARG(B > 0 && C > 0, "pwa_partition/reverse: bad B=%d C=%d", B, C);
   PWA_CHECK_ARG(dtype == PWA_F32 || dtype == PWA_BF16, "pwa_partition/reverse: bad dtype %d", dtype);
@@ -548,23 +578,28 @@ static int run(bool is_partition, const void* src, void* dst, int B, int C, cons
   // `use_crop_lo & 2` forces the generic kernel, `& 4` the word kernel (tests cross-check the three paths)
   if (use_crop_lo & 2) fast = vec = false;
   if (use_crop_lo & 4) vec = false;
-  if (((uintptr_t)src | (uintptr_t)dst) & 3) fast = false;   // staged paths move aligned 32-bit words
-  if (((uintptr_t)src | (uintptr_t)dst) & 15) vec = false;   // ... or aligned 16-byte vectors
+  if (((uintptr_t)src | (uintptr_t)src2 | (uintptr_t)dst) & 3) fast = false;   // staged paths move aligned 32-bit words
+  if (((uintptr_t)src | (uintptr_t)src2 | (uintptr_t)dst) & 15) vec = false;   // ... or aligned 16-byte vectors
   cudaStream_t st = (cudaStream_t)stream;
-  if (fast && vec) return eb == 4 ? launch_vec<4>(is_partition, src, dst, p, st) : launch_vec<2>(is_partition, src, dst, p, st);
-  if (fast) return eb == 4 ? launch_fast<4>(is_partition, src, dst, p, st) : launch_fast<2>(is_partition, src, dst, p, st);
-  return eb == 4 ? launch_generic<uint32_t>(is_partition, src, dst, p, st)
-                 : launch_generic<uint16_t>(is_partition, src, dst, p, st);
+  if (fast && vec) return eb == 4 ? launch_vec<4>(is_partition, src, src2, dst, p, st) : launch_vec<2>(is_partition, src, src2, dst, p, st);
+  if (fast) return eb == 4 ? launch_fast<4>(is_partition, src, src2, dst, p, st) : launch_fast<2>(is_partition, src, src2, dst, p, st);
+  return eb == 4 ? launch_generic<uint32_t>(is_partition, src, src2, dst, p, st)
+                 : launch_generic<uint16_t>(is_partition, src, src2, dst, p, st);
 }
 
 }  // namespace pwa
 
 extern "C" int pwa_partition(const void* x, void* tokens, int B, int C, const pwa_geom* g, int use_crop_lo, int dtype,
                              void* stream) {
-  return pwa::run(true, x, tokens, B, C, g, use_crop_lo, dtype, stream);
+  return pwa::run(true, x, nullptr, tokens, B, C, g, use_crop_lo, dtype, stream);
 }
 
 extern "C" int pwa_reverse(const void* tokens, void* x, int B, int C, const pwa_geom* g, int use_crop_lo, int dtype,
                            void* stream) {
-  return pwa::run(false, tokens, x, B, C, g, use_crop_lo, dtype, stream);
+  return pwa::run(false, tokens, nullptr, x, B, C, g, use_crop_lo, dtype, stream);
+}
+
+extern "C" int pwa_reverse_add(const void* tokens_a, const void* tokens_b, void* x, int B, int C, const pwa_geom* g,
+                               int use_crop_lo, int dtype, void* stream) {
+  return pwa::run(false, tokens_a, tokens_b, x, B, C, g, use_crop_lo, dtype, stream);
 }

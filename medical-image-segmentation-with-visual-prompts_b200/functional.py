@@ -123,6 +123,33 @@ class _Reverse(torch.autograd.Function):
         return _partition_raw(g.contiguous(), ctx.geom, 1), None
 
 
+class _ReverseAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, tok_a, tok_b, geom):
+        ctx.geom = geom
+        tok_a, tok_b = tok_a.contiguous(), tok_b.contiguous()
+        B, _, _, Cc = tok_a.shape
+        out = torch.empty((B, Cc, *geom.dims), dtype=tok_a.dtype, device=tok_a.device)
+        with torch.cuda.device(tok_a.device), _timed("reverse", 1, 3.0 * tok_a.numel() * tok_a.element_size(), tok_a):
+            rc = _lib.lib.pwa_reverse_add(_ptr(tok_a), _ptr(tok_b), _ptr(out), B, Cc, geom.ref(), 1, _dtype_code(tok_a),
+                                          _stream(tok_a))
+        _lib.check(rc, "pwa_reverse_add")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        d = _partition_raw(g.contiguous(), ctx.geom, 1)
+        return d, d, None
+
+
+def reverse_add_tokens(tok_a: torch.Tensor, tok_b: torch.Tensor, geom: Geometry) -> torch.Tensor:
+    """reverse_tokens(tok_a + tok_b) in one kernel (the block's last residual add, swin_block.py:227)."""
+    _require_cuda(tok_a, tok_b)
+    if tok_a.shape != tok_b.shape or tok_a.dtype != tok_b.dtype or tuple(tok_a.shape[1:3]) != (geom.P, geom.N):
+        raise ValueError("reverse_add_tokens: mismatching token tensors")
+    return _ReverseAdd.apply(tok_a, tok_b, geom)
+
+
 def partition_tokens(x: torch.Tensor, geom: Geometry) -> torch.Tensor:
     """[B,C,H,W,D] -> [B,P,N,C]: zero-pad, roll by -shift, strided window partition, channels last."""
     _require_cuda(x)
@@ -145,9 +172,10 @@ def reverse_tokens(tok: torch.Tensor, geom: Geometry) -> torch.Tensor:
 IMPL_AUTO, IMPL_F32, IMPL_TC = 0, 1, 2
 
 
-def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0):
+def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0):
     s = _lib.PwaAttnShape()
     s.B, s.P, s.C, s.heads, s.I = B, P, Cc, heads, I
+    s.ld_qkv, s.ld_p = ld_qkv, ld_p
     s.ws[0], s.ws[1], s.ws[2] = ws
     s.scale, s.p_drop, s.seed, s.offset = float(scale), float(p_drop), int(seed), int(offset)
     return s
@@ -276,3 +304,188 @@ def add_layer_norm(x, res, gamma, beta, eps: float = 1e-6):
 
 def layer_norm_supported(C: int) -> bool:
     return C % 4 == 0 and C <= 1024
+
+
+# ------------------------------------------------------------------------------------------------
+# relative-position bias tables
+# ------------------------------------------------------------------------------------------------
+class _BiasTables(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc_h, enc_w, enc_d, wc_h, wc_w, wc_d, enc_tok, w_tok, ws):
+        ten = [t.detach().float().contiguous() for t in (enc_h, enc_w, enc_d, wc_h, wc_w, wc_d)]
+        has_tok = enc_tok is not None
+        tk = [t.detach().float().contiguous() for t in (enc_tok, w_tok)] if has_tok else [None, None]
+        heads, E = ten[3].shape
+        I = tk[0].shape[0] if has_tok else 0
+        dev = ten[0].device
+        f32 = dict(dtype=torch.float32, device=dev)
+        th, tw, td = (torch.empty((heads, w, w), **f32) for w in ws)
+        tok = torch.empty((heads, I), **f32) if has_tok else None
+        a3 = C.c_int32 * 3
+        cap = a3(*[(t.shape[0] + 1) // 2 for t in ten[:3]])
+        wsa = a3(*ws)
+        with torch.cuda.device(dev), _timed("bias_tables_fwd", 1, 0.0, ten[0]):
+            rc = _lib.lib.pwa_bias_tables_fwd(*[_ptr(t) for t in ten], _ptr(tk[0]), _ptr(tk[1]), _ptr(th), _ptr(tw),
+                                              _ptr(td), _ptr(tok), heads, E, wsa, cap, I, _stream(ten[0]))
+        _lib.check(rc, "pwa_bias_tables_fwd")
+        ctx.save_for_backward(*ten, *([tk[0], tk[1]] if has_tok else []))
+        ctx.meta = (tuple(ws), has_tok, [t.dtype for t in (enc_h, enc_w, enc_d, wc_h, wc_w, wc_d)])
+        if not has_tok:
+            ctx.mark_non_differentiable()
+            return th, tw, td
+        return th, tw, td, tok
+
+    @staticmethod
+    def backward(ctx, *g):
+        ws, has_tok, dts = ctx.meta
+        saved = ctx.saved_tensors
+        ten, tk = list(saved[:6]), (list(saved[6:8]) if has_tok else [None, None])
+        heads, E = ten[3].shape
+        I = tk[0].shape[0] if has_tok else 0
+        grads = [None if x is None else x.contiguous().float() for x in g]
+        shapes = [(heads, w, w) for w in ws]
+        for i in range(3):
+            if grads[i] is None:
+                grads[i] = torch.zeros(shapes[i], dtype=torch.float32, device=ten[0].device)
+        dtok = None
+        if has_tok:
+            dtok = grads[3] if grads[3] is not None else torch.zeros((heads, I), dtype=torch.float32, device=ten[0].device)
+        outs = [torch.empty_like(t) for t in ten]
+        dtk = [torch.empty_like(t) for t in tk] if has_tok else [None, None]
+        a3 = C.c_int32 * 3
+        cap = a3(*[(t.shape[0] + 1) // 2 for t in ten[:3]])
+        with torch.cuda.device(ten[0].device), _timed("bias_tables_bwd", 1, 0.0, ten[0]):
+            rc = _lib.lib.pwa_bias_tables_bwd(*[_ptr(t) for t in ten], _ptr(tk[0]), _ptr(tk[1]), _ptr(grads[0]),
+                                              _ptr(grads[1]), _ptr(grads[2]), _ptr(dtok), *[_ptr(t) for t in outs],
+                                              _ptr(dtk[0]), _ptr(dtk[1]), heads, E, a3(*ws), cap, I, _stream(ten[0]))
+        _lib.check(rc, "pwa_bias_tables_bwd")
+        outs = [o.to(d) for o, d in zip(outs, dts)]
+        return (*outs, dtk[0], dtk[1], None)
+
+
+def bias_tables(enc_h, enc_w, enc_d, wc_h, wc_w, wc_d, enc_tok, w_tok, ws):
+    """Compact relative-position bias (th, tw, td, tok|None) on the pwa kernel; see include/pwa.h."""
+    _require_cuda(enc_h, enc_w, enc_d, wc_h, wc_w, wc_d, enc_tok, w_tok)
+    out = _BiasTables.apply(enc_h, enc_w, enc_d, wc_h, wc_w, wc_d, enc_tok, w_tok, tuple(int(w) for w in ws))
+    return out if len(out) == 4 else (*out, None)
+
+
+# ------------------------------------------------------------------------------------------------
+# packed variant: q|k|v are the column blocks of one fused projection output
+# ------------------------------------------------------------------------------------------------
+class _WindowAttentionPacked(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, kvp, th, tw, td, tok, ids, heads, ws, scale, impl):
+        qkv = qkv.contiguous()
+        B, P, N, C3 = qkv.shape
+        Cc = C3 // 3
+        I = 0 if kvp is None else kvp.shape[1]
+        es = qkv.element_size()
+        if kvp is not None:
+            kvp, tok = kvp.contiguous(), tok.contiguous().float()
+        th, tw, td = th.contiguous().float(), tw.contiguous().float(), td.contiguous().float()
+        out = torch.empty((B, P, N, Cc), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=qkv.device)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, ld_qkv=C3, ld_p=2 * Cc)
+        q0 = qkv.data_ptr()
+        p0 = 0 if kvp is None else kvp.data_ptr()
+        vpp = C.c_void_p
+        with torch.cuda.device(qkv.device), _timed("attn_fwd", 1, 4.0 * B * P * N * (N + I) * Cc, qkv):
+            rc = _lib.lib.pwa_attn_fwd(vpp(q0), vpp(q0 + Cc * es), vpp(q0 + 2 * Cc * es), vpp(p0), vpp(p0 + Cc * es if p0 else 0),
+                                       _ptr(th), _ptr(tw), _ptr(td), _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), C.byref(s),
+                                       _dtype_code(qkv), impl, _stream(qkv))
+        _lib.check(rc, "pwa_attn_fwd")
+        ctx.save_for_backward(qkv, kvp, th, tw, td, tok, ids, out, lse)
+        ctx.meta = (heads, tuple(ws), scale, impl, I)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, kvp, th, tw, td, tok, ids, out, lse = ctx.saved_tensors
+        heads, ws, scale, impl, I = ctx.meta
+        B, P, N, C3 = qkv.shape
+        Cc = C3 // 3
+        es = qkv.element_size()
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        f32 = dict(dtype=torch.float32, device=qkv.device)
+        dkvp32 = torch.empty((2, B, I, Cc), **f32) if I else None
+        dth, dtw, dtd = torch.empty_like(th), torch.empty_like(tw), torch.empty_like(td)
+        dtok = torch.empty_like(tok) if I else None
+        delta = torch.empty_like(lse)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, ld_qkv=C3, ld_p=2 * Cc)
+        q0, d0 = qkv.data_ptr(), dqkv.data_ptr()
+        p0 = 0 if kvp is None else kvp.data_ptr()
+        vpp = C.c_void_p
+        with torch.cuda.device(qkv.device), _timed("attn_bwd", 2, 8.0 * B * P * N * (N + I) * Cc, qkv):
+            rc = _lib.lib.pwa_attn_bwd(vpp(q0), vpp(q0 + Cc * es), vpp(q0 + 2 * Cc * es), vpp(p0), vpp(p0 + Cc * es if p0 else 0),
+                                       _ptr(th), _ptr(tw), _ptr(td), _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), _ptr(dout),
+                                       vpp(d0), vpp(d0 + Cc * es), vpp(d0 + 2 * Cc * es),
+                                       _ptr(dkvp32[0] if I else None), _ptr(dkvp32[1] if I else None),
+                                       _ptr(dth), _ptr(dtw), _ptr(dtd), _ptr(dtok), _ptr(delta), C.byref(s),
+                                       _dtype_code(qkv), impl, _stream(qkv))
+        _lib.check(rc, "pwa_attn_bwd")
+        dkvp = None
+        if I:
+            dkvp = torch.cat([dkvp32[0], dkvp32[1]], dim=-1).to(qkv.dtype)          # [B,I,2C]
+        return dqkv, dkvp, dth, dtw, dtd, dtok, None, None, None, None, None
+
+
+def prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads: int, ws: Sequence[int], scale: float,
+                                     impl: int = IMPL_AUTO) -> torch.Tensor:
+    """qkv [B,P,N,3C] = [q | k | v] of one fused projection; kvp [B,I,2C] = [kp | vp] or None."""
+    _require_cuda(qkv, kvp, th, tw, td, tok, ids)
+    if qkv.shape[-1] % (3 * heads) != 0:
+        raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
+    return _WindowAttentionPacked.apply(qkv, kvp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl)
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear layers with fp32 master weights and bf16/fp32 activations (cuBLAS GEMMs; plain library calls)
+# ------------------------------------------------------------------------------------------------
+def _mm_f32(a, b):
+    """a @ b accumulated and returned in fp32 (no bf16 round trip of weight gradients)."""
+    if a.dtype == torch.float32:
+        return torch.mm(a, b)
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.mm(a, b).float()
+
+
+class _MultiLinear(torch.autograd.Function):
+    """y = x @ cat(weights)^T (+ bias): several nn.Linear weights that share an input, as ONE GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, bias, *weights):
+        w = (weights[0] if len(weights) == 1 else torch.cat(weights, dim=0)).detach().to(x.dtype)
+        x2 = x.reshape(-1, x.shape[-1])
+        if bias is not None:
+            y = torch.addmm(bias.detach().to(x.dtype), x2, w.t())
+        else:
+            y = torch.mm(x2, w.t())
+        ctx.save_for_backward(x2, w)
+        ctx.meta = (x.shape, [wt.shape[0] for wt in weights], [wt.dtype for wt in weights],
+                    None if bias is None else bias.dtype)
+        return y.reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        xshape, rows, wdts, bdt = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dx = torch.mm(dy2, w).reshape(xshape) if ctx.needs_input_grad[0] else None
+        db = dy2.sum(dim=0, dtype=torch.float32).to(bdt) if bdt is not None and ctx.needs_input_grad[1] else None
+        dws = [None] * len(rows)
+        if any(ctx.needs_input_grad[2:]):
+            dw = _mm_f32(dy2.t(), x2)
+            o = 0
+            for i, r in enumerate(rows):
+                if ctx.needs_input_grad[2 + i]:
+                    dws[i] = dw[o:o + r].to(wdts[i])
+                o += r
+        return (dx, db, *dws)
+
+
+def multi_linear(x, bias, *weights):
+    return _MultiLinear.apply(x, bias, *weights)

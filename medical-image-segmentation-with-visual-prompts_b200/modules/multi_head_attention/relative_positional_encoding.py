@@ -44,6 +44,20 @@ class RelativePE(nn.Module):
     def tables(self, dim_h: int, dim_w: int, dim_d: int, dim_i: int = 0):
         """(th [h,dim_h,dim_h], tw, td, tok [h,dim_i] | None), fp32, including the /3 and
         embed_dim**-0.5 factors (reference :116-123, :136-138)."""
+        if self.enc_content_h.is_cuda:
+            # one pwa kernel launch (csrc/bias.cu) instead of ~10 tiny torch ops (and ~25 in backward)
+            from ... import functional as PF
+            enc_tok = w_tok = None
+            if dim_i > 0:
+                enc_tok = self.enc_token[0] if len(self.enc_token) == 1 else torch.cat(list(self.enc_token), dim=0)
+                if enc_tok.shape[0] != dim_i:
+                    raise RuntimeError(f"RelativePE: {dim_i} prompt tokens given but max_prompts*tokens_per_prompt = "
+                                       f"{enc_tok.shape[0]}")
+                w_tok = self.weights_token
+            dims = (dim_h, dim_w, dim_d)
+            if all(getattr(self, f"relative_dist_{ax}").shape[0] >= n for ax, n in zip(_AXES, dims)):
+                return PF.bias_tables(self.enc_content_h, self.enc_content_w, self.enc_content_d, self.weights_content_h,
+                                      self.weights_content_w, self.weights_content_d, enc_tok, w_tok, dims)
         out = []
         for ax, n in zip(_AXES, (dim_h, dim_w, dim_d)):
             enc = getattr(self, f"enc_content_{ax}")

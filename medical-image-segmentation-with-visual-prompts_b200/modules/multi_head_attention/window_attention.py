@@ -52,13 +52,22 @@ class WindowAttention(nn.Module):
                                       "position bias (RelativePE.tables), not a dense [1,1,h,N',N'] tensor")
         if self.training and self.attn_drop.p > 0:
             raise NotImplementedError("attn_drop > 0 in training mode is not implemented in the fused kernel yet")
-        dt = q.dtype
-        wq, wk, wv = (w.weight.to(dt) for w in (self.to_q, self.to_k, self.to_v))
-        qq, kk, vv = F.linear(q, wq), F.linear(k, wk), F.linear(v, wv)
-        kp = vp = None
-        if prompts is not None:
-            kp, vp = F.linear(prompts, wk), F.linear(prompts, wv)
-        o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
-                                         self.num_heads, pos_bias.ws, self.scale, self.impl)
-        o = F.linear(o, self.proj.weight.to(dt), self.proj.bias.to(dt))
+        if q is k and k is v:
+            # self-attention (the only way the block calls it): ONE fused [C -> 3C] projection GEMM; the kernels
+            # read q|k|v as column blocks of its output (row stride 3C), prompt K/V likewise from [C -> 2C]
+            qkv = PF.multi_linear(q, None, self.to_q.weight, self.to_k.weight, self.to_v.weight)
+            kvp = PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight) if prompts is not None else None
+            o = PF.prompted_window_attention_packed(qkv, kvp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
+                                                    self.num_heads, pos_bias.ws, self.scale, self.impl)
+        else:
+            qq = PF.multi_linear(q, None, self.to_q.weight)
+            kk = PF.multi_linear(k, None, self.to_k.weight)
+            vv = PF.multi_linear(v, None, self.to_v.weight)
+            kp = vp = None
+            if prompts is not None:
+                kp = PF.multi_linear(prompts, None, self.to_k.weight)
+                vp = PF.multi_linear(prompts, None, self.to_v.weight)
+            o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok,
+                                             mask, self.num_heads, pos_bias.ws, self.scale, self.impl)
+        o = PF.multi_linear(o, self.proj.bias, self.proj.weight)
         return self.proj_drop(o)

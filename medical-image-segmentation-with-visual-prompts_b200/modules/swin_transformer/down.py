@@ -33,9 +33,10 @@ class PatchMerging(nn.Module):
         from ... import functional as PF
         if t.is_cuda and PF.layer_norm_supported(t.shape[-1]):
             t = PF.layer_norm(t.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps)
+            t = PF.multi_linear(t, None, self.reduction.weight)
         else:
             t = F.layer_norm(t, self.norm.normalized_shape, self.norm.weight.to(dt), self.norm.bias.to(dt), self.norm.eps)
-        t = F.linear(t, self.reduction.weight.to(dt))
+            t = F.linear(t, self.reduction.weight.to(dt))
         return t.permute(0, 4, 1, 2, 3).contiguous()
 
     def named_parameters_body(self):

@@ -132,8 +132,8 @@ class SwinTransformerBlock(nn.Module):
                               prompts=prompts)
                 y = y + xw
                 z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
-            y = y + F.linear(z, self.mlp.weight.to(cdt), self.mlp.bias.to(cdt))
-            out = PF.reverse_tokens(y, geom)                                # [B,C,H,W,D]
+            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight)
+            out = PF.reverse_add_tokens(y, m, geom)                         # reverse(y + mlp(LN2(y))) -> [B,C,H,W,D]
         return out.to(in_dtype)
 
     def forward(self, x, p=None):

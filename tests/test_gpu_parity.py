@@ -301,3 +301,29 @@ def test_layer_norm_kernels(C, dtype, rtol, with_res):
     assert rel_linf(xd.grad, x64.grad) < rtol
     assert rel_linf(gd.grad, g64.grad) < rtol
     assert rel_linf(bd.grad, b64.grad) < rtol
+
+
+def test_bias_tables_kernel_vs_reference_golden():
+    """RelativePE on the pwa kernel: dense bias against the live reference's output, and gradients of all eight
+    parameter tensors against torch autograd of the CPU formulation (float64)."""
+    from tests.util import load_npz
+    d = load_npz("pe_small")
+    sd = {k[3:]: torch.from_numpy(v) for k, v in d.items() if k.startswith("sd.")}
+    mk = lambda: pwa_b200.RelativePE(embed_dim=16, num_heads=3, max_abs_pos=(4, 4, 2), max_cap_dist=(4, 4, 2),
+                                     max_prompts=2, tokens_per_prompt=3)
+    pe_gpu, pe_cpu = mk(), mk().double()
+    pe_gpu.load_state_dict({k: v.float() if v.is_floating_point() else v for k, v in sd.items()})
+    pe_cpu.load_state_dict(sd)
+    pe_gpu.to(DEV)
+    dense = pe_gpu(4, 4, 2, 6)
+    assert rel_linf(dense, torch.from_numpy(d["bias_prompt"])) < 1e-6
+    assert rel_linf(pe_gpu(4, 4, 2, 0), torch.from_numpy(d["bias_content"])) < 1e-6
+    gen = torch.Generator().manual_seed(0)
+    gs = [torch.randn(3, 4, 4, generator=gen), torch.randn(3, 4, 4, generator=gen), torch.randn(3, 2, 2, generator=gen),
+          torch.randn(3, 6, generator=gen)]
+    out_g = pe_gpu.tables(4, 4, 2, 6)
+    sum((o * g.to(DEV)).sum() for o, g in zip(out_g, gs)).backward()
+    out_c = pe_cpu.tables(4, 4, 2, 6)
+    sum((o * g.double()).sum() for o, g in zip(out_c, gs)).backward()
+    for (n, pg), (_, pc) in zip(pe_gpu.named_parameters(), pe_cpu.named_parameters()):
+        assert rel_linf(pg.grad, pc.grad) < 1e-5, n

@@ -32,7 +32,7 @@ struct PartParams {
   int nchunk;    // C / CT
   int pitch;     // smem row pitch in 32-bit words (odd)
   int padded;
-  FastDiv div_cw, div_wwwd, div_wd, div_dq, div_ww;
+  FastDiv div_cw, div_wwwd, div_wd, div_dq, div_ww, div_ndg;   // div_ndg: d-vector groups per line (vector kernels)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -164,7 +164,8 @@ __global__ void __launch_bounds__(256) partition_fast_kernel(const uint32_t* __r
       uint32_t line, dq, cw, t2;
       p.div_dq.divmod(i, line, dq);
       p.div_ww.divmod(line, cw, t2);
-      int w = (int)(t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      int w = (int)(t2 * p.P2) + s.p2 + p.sw;
+      w = (w >= p.Wp ? w - p.Wp : w) - p.low;
       if (w < 0 || w >= p.W) continue;
       if (EB == 4) {
         size_t g = base_b + (size_t)cw * plane + (size_t)w * p.D + dq;
@@ -252,7 +253,8 @@ __global__ void __launch_bounds__(256) reverse_fast_kernel(const uint32_t* __res
       uint32_t line, dq, cw, t2;
       p.div_dq.divmod(i, line, dq);
       p.div_ww.divmod(line, cw, t2);
-      int w = (int)(t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      int w = (int)(t2 * p.P2) + s.p2 + p.sw;
+      w = (w >= p.Wp ? w - p.Wp : w) - p.low;
       if (w < 0 || w >= p.W) continue;
       if (EB == 4) {
         int r = roll_fwd(dq, p.lod, p.sd, p.Dp);
@@ -304,7 +306,7 @@ __device__ __forceinline__ TokMap make_tok_map(const PartParams& p, int CW, int 
 #pragma unroll
   for (int k = 0; k < kTokK; ++k) {
     const int idx = lane + 32 * k;
-    const int t3 = idx / CW, cw = idx - t3 * CW;
+    const int t3 = (int)p.div_cw.div((uint32_t)idx), cw = idx - t3 * CW;
     const bool ok = idx < total;
     m.soff[k] = ok ? t3 * p.P3 * p.pitch + cw : -1;
     m.goff[k] = t3 * tok_w + cw;
@@ -335,10 +337,11 @@ __global__ void __launch_bounds__(256) partition_vec_kernel(const uint32_t* __re
     const size_t plane_w = plane / V::CPW;                  // words per channel plane
     const int cl = lane % V::CL, dl = lane / V::CL;
     for (int it = warp; it < items; it += 8) {
-      const int dg = it % n_dg;
-      const int r = it / n_dg;
-      const int t2 = r % p.ww, cg = r / p.ww;
-      const int w = (t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      uint32_t r, dg, cg, t2;
+      p.div_ndg.divmod((uint32_t)it, r, dg);
+      p.div_ww.divmod(r, cg, t2);
+      int w = (int)t2 * p.P2 + s.p2 + p.sw;          // < 2 * Wp
+      w = (w >= p.Wp ? w - p.Wp : w) - p.low;
       const int cw = cg * V::CL + cl, dvec = dg * V::DL + dl;
       if (w < 0 || w >= p.W || cw >= CW || dvec >= DV) continue;
       int rr = roll_fwd(dvec * V::EPV, p.lod, p.sd, p.Dp);
@@ -376,7 +379,8 @@ __global__ void __launch_bounds__(256) partition_vec_kernel(const uint32_t* __re
     const size_t cw0 = (size_t)s.chunk * CW;
     const int items = p.P3 * p.ww;
     for (int it = warp; it < items; it += 8) {
-      const int t2 = it % p.ww, p3 = it / p.ww;
+      uint32_t p3, t2;
+      p.div_ww.divmod((uint32_t)it, p3, t2);
       const uint32_t* sb = smem + (t2 * p.Dp + p3) * p.pitch;
       uint32_t* gb = tok + ((win0 + p3) * p.N + row0 + (size_t)t2 * p.wd) * tok_w + cw0;
 #pragma unroll
@@ -404,7 +408,8 @@ __global__ void __launch_bounds__(256) reverse_vec_kernel(const uint32_t* __rest
     const size_t cw0 = (size_t)s.chunk * CW;
     const int items = p.P3 * p.ww;
     for (int it = warp; it < items; it += 8) {
-      const int t2 = it % p.ww, p3 = it / p.ww;
+      uint32_t p3, t2;
+      p.div_ww.divmod((uint32_t)it, p3, t2);
       uint32_t* sb = smem + (t2 * p.Dp + p3) * p.pitch;
       const size_t goff0 = ((win0 + p3) * p.N + row0 + (size_t)t2 * p.wd) * tok_w + cw0;
       const uint32_t* gb = tok + goff0;
@@ -428,10 +433,11 @@ __global__ void __launch_bounds__(256) reverse_vec_kernel(const uint32_t* __rest
     const size_t plane_w = plane / V::CPW;
     const int cl = lane % V::CL, dl = lane / V::CL;
     for (int it = warp; it < items; it += 8) {
-      const int dg = it % n_dg;
-      const int r = it / n_dg;
-      const int t2 = r % p.ww, cg = r / p.ww;
-      const int w = (t2 * p.P2 + s.p2 + p.sw) % p.Wp - p.low;
+      uint32_t r, dg, cg, t2;
+      p.div_ndg.divmod((uint32_t)it, r, dg);
+      p.div_ww.divmod(r, cg, t2);
+      int w = (int)t2 * p.P2 + s.p2 + p.sw;          // < 2 * Wp
+      w = (w >= p.Wp ? w - p.Wp : w) - p.low;
       const int cw = cg * V::CL + cl, dvec = dg * V::DL + dl;
       if (w < 0 || w >= p.W || cw >= CW || dvec >= DV) continue;
       int rr = roll_fwd(dvec * V::EPV, p.lod, p.sd, p.Dp);
@@ -498,6 +504,8 @@ static int fill_params(PartParams& p, int B, int C, const pwa_geom* g, int use_c
     p.div_wd = FastDiv(p.wd);
     p.div_dq = FastDiv(p.D / epw);
     p.div_ww = FastDiv(p.ww);
+    const int dl = eb == 2 ? 4 : 8, dv = p.D / (16 / eb);
+    p.div_ndg = FastDiv((dv + dl - 1) / dl > 0 ? (dv + dl - 1) / dl : 1);
   }
   *fast = ok;
   // vector path: whole 16-byte vectors along D, token runs that fit the per-lane offset table

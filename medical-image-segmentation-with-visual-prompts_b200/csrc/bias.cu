@@ -30,39 +30,40 @@ __device__ __forceinline__ int rel_index(int i, int j, int cap) {
   return r > mx ? mx : r;
 }
 
-// grid.x = 4 (three content axes + token), block = 256
+// grid = (4 [three content axes + token], heads), block = 256
 __global__ void __launch_bounds__(256) bias_tables_fwd_kernel(BiasArgs a) {
-  extern __shared__ float sm[];                                  // per_dist [heads][R]
-  const int ax = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ float sm[];                                  // per_dist [R] of this head
+  const int ax = blockIdx.x, hd = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float scale = rsqrtf((float)a.E);
   if (ax < 3) {
     const int w = a.ws[ax], cap = a.cap[ax], R = 2 * cap - 1;
-    for (int o = warp; o < a.heads * R; o += 8) {
-      const int hd = o / R, r = o - hd * R;
+    for (int r = warp; r < R; r += 8) {
       float s = 0.f;
       for (int c = lane; c < a.E; c += 32) s = fmaf(a.wc[ax][hd * a.E + c], a.enc[ax][r * a.E + c], s);
       s = warp_sum(s);
-      if (lane == 0) sm[o] = s * (scale / 3.f);
+      if (lane == 0) sm[r] = s * (scale / 3.f);
     }
     __syncthreads();
-    for (int o = tid; o < a.heads * w * w; o += 256) {
-      const int hd = o / (w * w), ij = o - hd * w * w, i = ij / w, j = ij - i * w;
-      a.tab[ax][o] = sm[hd * R + rel_index(i, j, cap)];
+    for (int ij = tid; ij < w * w; ij += 256) {
+      const int i = ij / w, j = ij - i * w;
+      a.tab[ax][hd * w * w + ij] = sm[rel_index(i, j, cap)];
     }
   } else if (a.I > 0) {
-    for (int o = warp; o < a.heads * a.I; o += 8) {
-      const int hd = o / a.I, i = o - hd * a.I;
+    for (int i = warp; i < a.I; i += 8) {
       float s = 0.f;
       for (int c = lane; c < a.E; c += 32) s = fmaf(a.w_tok[hd * a.E + c], a.enc_tok[i * a.E + c], s);
       s = warp_sum(s);
-      if (lane == 0) a.tok[o] = s * scale;
+      if (lane == 0) a.tok[hd * a.I + i] = s * scale;
     }
   }
 }
 
+// grid = (4, kBwdSplit): every block rebuilds the tiny dper table, then owns a slice of the output elements
+constexpr int kBwdSplit = 16;
 __global__ void __launch_bounds__(256) bias_tables_bwd_kernel(BiasArgs a) {
   extern __shared__ float sm[];                                  // dper [heads][R] (content) / unused (token)
   const int ax = blockIdx.x, tid = threadIdx.x;
+  const int gt = blockIdx.y * 256 + tid, gn = kBwdSplit * 256;   // thread id / count across the blockIdx.y slices
   const float scale = rsqrtf((float)a.E);
   if (ax < 3) {
     const int w = a.ws[ax], cap = a.cap[ax], R = 2 * cap - 1;
@@ -74,28 +75,29 @@ __global__ void __launch_bounds__(256) bias_tables_bwd_kernel(BiasArgs a) {
       atomicAdd(&sm[hd * R + rel_index(i, j, cap)], a.tab[ax][o]);
     }
     __syncthreads();
-    for (int o = tid; o < R * a.E; o += 256) {                   // d enc[r][c] = f * sum_h dper[h][r] * W[h][c]
+    for (int o = gt; o < R * a.E; o += gn) {                     // d enc[r][c] = f * sum_h dper[h][r] * W[h][c]
       const int r = o / a.E, c = o - r * a.E;
       float s = 0.f;
       for (int hd = 0; hd < a.heads; ++hd) s = fmaf(sm[hd * R + r], a.wc[ax][hd * a.E + c], s);
       a.denc[ax][o] = s * f;
     }
-    for (int o = tid; o < a.heads * a.E; o += 256) {             // d W[h][c] = f * sum_r dper[h][r] * enc[r][c]
+    for (int o = gt; o < a.heads * a.E; o += gn) {               // d W[h][c] = f * sum_r dper[h][r] * enc[r][c]
       const int hd = o / a.E, c = o - hd * a.E;
       float s = 0.f;
       for (int r = 0; r < R; ++r) s = fmaf(sm[hd * R + r], a.enc[ax][r * a.E + c], s);
       a.dwc[ax][o] = s * f;
     }
   } else if (a.I > 0) {
-    for (int o = tid; o < a.I * a.E; o += 256) {
+    for (int o = gt; o < a.I * a.E; o += gn) {
       const int i = o / a.E, c = o - i * a.E;
       float s = 0.f;
       for (int hd = 0; hd < a.heads; ++hd) s = fmaf(a.tok[hd * a.I + i], a.w_tok[hd * a.E + c], s);
       a.denc_tok[o] = s * scale;
     }
-    for (int o = tid; o < a.heads * a.E; o += 256) {
+    for (int o = gt; o < a.heads * a.E; o += gn) {
       const int hd = o / a.E, c = o - hd * a.E;
       float s = 0.f;
+#pragma unroll 8
       for (int i = 0; i < a.I; ++i) s = fmaf(a.tok[hd * a.I + i], a.enc_tok[i * a.E + c], s);
       a.dw_tok[o] = s * scale;
     }
@@ -131,7 +133,7 @@ extern "C" int pwa_bias_tables_fwd(const float* enc_h, const float* enc_w, const
   for (int x = 0; x < 3; ++x) { a.ws[x] = ws[x]; a.cap[x] = cap[x]; maxR = max(maxR, 2 * cap[x] - 1); }
   int rc = check_common(a, "pwa_bias_tables_fwd");
   if (rc != PWA_OK) return rc;
-  bias_tables_fwd_kernel<<<4, 256, (size_t)heads * maxR * 4, (cudaStream_t)stream>>>(a);
+  bias_tables_fwd_kernel<<<dim3(4, heads), 256, (size_t)maxR * 4, (cudaStream_t)stream>>>(a);
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }
@@ -159,7 +161,7 @@ extern "C" int pwa_bias_tables_bwd(const float* enc_h, const float* enc_w, const
   if (rc != PWA_OK) return rc;
   for (int x = 0; x < 3; ++x) PWA_CHECK_ARG(a.denc[x] && a.dwc[x], "pwa_bias_tables_bwd: null gradient pointer");
   PWA_CHECK_ARG(I == 0 || (denc_tok && dw_tok), "pwa_bias_tables_bwd: null token gradient pointer");
-  bias_tables_bwd_kernel<<<4, 256, (size_t)heads * maxR * 4, (cudaStream_t)stream>>>(a);
+  bias_tables_bwd_kernel<<<dim3(4, kBwdSplit), 256, (size_t)heads * maxR * 4, (cudaStream_t)stream>>>(a);
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }

@@ -4,25 +4,31 @@
 // this head's Q / K / V slices in shared memory in UMMA canonical (no-swizzle) layouts, then for each of the
 // two 128-row query tiles and each key block (content 0-127, content 128-255, prompt 0-I):
 //     S[128 x nk]  = Q'.K'^T            tcgen05.mma kind::f16, both operands from smem, fp32 accum in TMEM
-//     P            = exp2(mask(S) - m)  each thread owns one query row = one TMEM lane (tcgen05.ld 32x32b),
+//     P            = exp2(S*c - mb)     each thread owns one query row = one TMEM lane (tcgen05.ld 32x32b),
 //                                       writes P back as packed bf16 over the consumed S columns (tcgen05.st)
-//     O[128 x dh] += P.V                tcgen05.mma with A = P straight from TMEM, B = V (MN-major) from smem
-// and merges the key blocks with a running (max, sum, O) per row in registers.
+//     O[128 x dh+1] = P.[V | 1]         tcgen05.mma with A = P straight from TMEM, B = V (MN-major) from smem;
+//                                       the ones column of V yields the softmax denominator for free
+// The softmax is bound by the MUFU pipe (one ex2 per logit; measured 28 ex2/clk/SM, csrc/ubench.cu), so the
+// per-logit instruction stream is kept to FFMA + MUFU + 1/2 F2FP(pack):
+//   * no row-max pass: the stabiliser mb of a row is the Cauchy-Schwarz bound c*(|q_i| max_j|k_j| + max bias),
+//     known before the first MMA.  Softmax is shift invariant, so the result is identical as long as nothing
+//     under/overflows; if a bound exceeds kMaxBound (never with LayerNorm-ed inputs) the CTA first makes an
+//     exact-max sweep over the three key blocks (MMA + TMEM loads only) and uses that instead.
+//   * no online rescaling: the same mb holds for all key blocks, partial O tiles are simply added.
+//   * the shift mask is multiplicative and applied BEFORE softmax (window_attention.py:54-56): a masked logit
+//     becomes 0, i.e. its probability is the row constant e0 = exp2(-mb).  It is applied on the PACKED bf16
+//     pairs with one PRMT per pair, selecting between the computed pair and (e0,e0) with byte selectors that
+//     depend only on (region id of the row, key pair): a [28 ids][128 pairs] table built once per window.
 //
 // Relative-position bias is folded INTO the QK^T MMA: bias[n][m] = Th[ih][jh] + Tw[iw][jw] + Td[id][jd] is a
 // sum of three one-hot x table products, so Q' = [q | onehot_d(n) | 0 ;; onehot_h(n) | onehot_w(n)] and
-// K' = [k | Td[.][jd]/scale | 0 ;; Th[.][jh]/scale | Tw[.][jw]/scale] give S = q.k + bias/scale.  The tensor
-// pipe has >8x headroom at head_dim 12 (the kernel is bound by MUFU/ALU softmax work), so the extra k-step is
-// free while it removes two FADDs + table lookups per logit from the CUDA cores.  Prompt keys use
+// K' = [k | Td[.][jd]/scale | 0 ;; Th[.][jh]/scale | Tw[.][jw]/scale] give S = q.k + bias/scale.  Prompt keys use
 // [tok/scale x wh | 0] so every query row picks up tok[i].  The one-hot / table halves do not depend on the
 // window, so they are built once per CTA and stay resident in smem, as do the prompt-independent constants.
 //
-// The shift mask is multiplicative and applied BEFORE softmax (window_attention.py:54-56): masked logits
-// become exactly 0 and still get weight exp(0 - max).  It is evaluated from uint8 region ids in smem.
-//
-// Four CTAs are resident per SM (128 TMEM columns and ~46 KB smem each at head_dim 12): while one CTA waits
-// for its MMAs or stages the next window, the others keep the MUFU/ALU pipes busy, so no intra-CTA
-// warp-specialised pipeline is needed.
+// Four CTAs are resident per SM (128 TMEM columns and ~54 KB smem each at head_dim 12): tcgen05.mma costs
+// ~100 clk of latency per instruction but streams of different CTAs overlap (csrc/ubench.cu), so while one
+// CTA waits for its MMAs or stages the next window, the others keep the MUFU pipe busy.
 #include "attn.cuh"
 #include "tc_common.cuh"
 
@@ -35,23 +41,32 @@ constexpr int kRows = 128;        // query rows per tile = TMEM lanes = threads 
 constexpr int kN = 256;           // content tokens per window (two query tiles, two content key blocks)
 constexpr int kTmemCols = 128;
 constexpr int kOCol = 64;         // O accumulator lives in columns [64, 64 + DHP) of the S region
+constexpr int kIds = 28;          // region ids 0..26 and 100 (-> 27), see pwa_region_ids
+constexpr float kMaxBound = 40.f; // log2 units: the largest exp2 argument of a row stays within [-2*kMaxBound, ~0]
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ int id_slot(uint32_t id) { return id < (uint32_t)(kIds - 1) ? (int)id : kIds - 1; }
 
 template <int DH> struct Cfg {
-  static constexpr int DHP = (DH + 15) / 16 * 16;          // V / O width (PV MMA N)
+  static constexpr int DHP = (DH + 1 + 15) / 16 * 16;      // V / O width (PV MMA N) incl. the ones column at DH
   static constexpr int NDC = DHP / 8;                      // 16-byte chunks per V row
+  static constexpr int KS = (DH + 4 + 15) / 16;            // k-steps of the staged [q | onehot_d] operand
 };
 
 struct TcSmem {
-  uint32_t q, k, v, qaug, kaug, ids, total;                // byte offsets
+  uint32_t q, k, v, qaug, kaug, sel, rowb, ids, total;     // byte offsets
 };
 
-__host__ __device__ inline TcSmem tc_layout(int KS, int DHP, int NKT) {
+__host__ __device__ inline TcSmem tc_layout(int KS, int DHP, int NKT, bool masked) {
   TcSmem s;
   uint32_t o = 0;
   s.q = o; o += KS * 2 * kN * 16;
@@ -59,6 +74,8 @@ __host__ __device__ inline TcSmem tc_layout(int KS, int DHP, int NKT) {
   s.v = o; o += NKT * DHP * 2;
   s.qaug = o; o += 2 * kN * 16;
   s.kaug = o; o += 2 * NKT * 16;
+  s.sel = o; o += masked ? kIds * (kN / 4) * 4 : 0;        // [id][pair of packed words] PRMT selectors
+  s.rowb = o; o += kN * 4;
   s.ids = o; o += kN;
   s.total = o;
   return s;
@@ -75,6 +92,17 @@ __device__ __forceinline__ void load_row(const __nv_bfloat16* src, __nv_bfloat16
 #pragma unroll
     for (int i = 0; i < DH; ++i) dst[i] = src[i];
   }
+}
+
+template <int DH>
+__device__ __forceinline__ float sumsq(const __nv_bfloat16 (&r)[DH]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) {
+    const float v = __bfloat162float(r[i]);
+    s = fmaf(v, v, s);
+  }
+  return s;
 }
 
 // staged K-dim layout of one head: [real DH | wd extra columns | zero pad] -> KS k-steps of 16
@@ -98,30 +126,32 @@ __device__ __forceinline__ void store_chunks(uint8_t* base, uint32_t chunk_strid
 }
 
 template <int DH, bool MASKED>
-__global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
-  constexpr int DHP = Cfg<DH>::DHP, NDC = Cfg<DH>::NDC;
-  constexpr int KS = (DH + 4 + 15) / 16;                   // wd <= 4 extra columns ride in the padding
+__global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) attn_fwd_tc_kernel(AttnParams p) {
+  constexpr int DHP = Cfg<DH>::DHP, NDC = Cfg<DH>::NDC, KS = Cfg<DH>::KS;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t kmax_s[4];
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NKT = kN + p.I;
-  const TcSmem L = tc_layout(KS, DHP, NKT);
+  const TcSmem L = tc_layout(KS, DHP, NKT, MASKED);
   uint8_t* Qs = smem + L.q;
   uint8_t* Ks = smem + L.k;
   uint8_t* Vs = smem + L.v;
   uint8_t* Qa = smem + L.qaug;
   uint8_t* Ka = smem + L.kaug;
+  uint32_t* sel_s = reinterpret_cast<uint32_t*>(smem + L.sel);
+  float* rowb_s = reinterpret_cast<float*>(smem + L.rowb);
   uint8_t* ids_s = smem + L.ids;
   const int head = blockIdx.x % p.heads;
   const float inv_scale = 1.f / p.scale;
   const float c2 = p.scale * 1.4426950408889634f;          // logits -> log2 domain
   const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
 
-  // ---- once per CTA: window-independent halves of Q' and K' ----
+  // ---- once per CTA: window-independent halves of Q' and K', per-row upper bound of the bias ----
   for (int n = tid; n < kN; n += kRows) {
-    const int iw = (n / p.wd) % p.ww, ih = n / (p.wd * p.ww);
+    const int id_ = n % p.wd, iw = (n / p.wd) % p.ww, ih = n / (p.wd * p.ww);
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
       __align__(16) __nv_bfloat16 tmp[8];
@@ -132,6 +162,12 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
       }
       *reinterpret_cast<uint4*>(Qa + c * (kN * 16) + n * 16) = *reinterpret_cast<const uint4*>(tmp);
     }
+    float bh = -1e30f, bw = -1e30f, bd = -1e30f, bt = -1e30f;
+    for (int j = 0; j < p.wh; ++j) bh = fmaxf(bh, p.th[(head * p.wh + ih) * p.wh + j]);
+    for (int j = 0; j < p.ww; ++j) bw = fmaxf(bw, p.tw[(head * p.ww + iw) * p.ww + j]);
+    for (int j = 0; j < p.wd; ++j) bd = fmaxf(bd, p.td[(head * p.wd + id_) * p.wd + j]);
+    for (int j = 0; j < p.I; ++j) bt = fmaxf(bt, p.tok[head * p.I + j]);
+    rowb_s[n] = (p.I > 0 ? fmaxf(bh + bw + bd, bt) : bh + bw + bd) * inv_scale;   // max_j bias[n][j] / scale
   }
   for (int j = tid; j < NKT; j += kRows) {
     const bool content = j < kN;
@@ -174,13 +210,34 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
   const int n_pairs = p.B * p.P;
   const int stride = gridDim.x / p.heads;
 
+  // S = Q'.K'^T for (query tile mt, key block kb); single thread
+  auto issue_s = [&](int mt, int kb) {
+    tc_fence_after();
+    const uint32_t idesc = kb < 2 ? idescS128 : idescSP;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const uint64_t da = make_smem_desc(smem_u32(Qs) + ks * 2 * (kN * 16) + mt * (kRows * 16), kN * 16, 128);
+      const uint64_t db = make_smem_desc(smem_u32(Ks) + ks * 2 * (NKT * 16) + kb * (128 * 16), NKT * 16, 128);
+      mma_ss(tmem, da, db, idesc, ks > 0);
+    }
+    const uint64_t da = make_smem_desc(smem_u32(Qa) + mt * (kRows * 16), kN * 16, 128);
+    const uint64_t db = make_smem_desc(smem_u32(Ka) + kb * (128 * 16), NKT * 16, 128);
+    mma_ss(tmem, da, db, idesc, 1);
+    mma_commit(&bar);
+  };
+
   for (int bw = blockIdx.x / p.heads; bw < n_pairs; bw += stride) {
     const int b = bw / p.P, win = bw - b * p.P;
-    // ---- stage this (window, head): Q, K (content + prompt rows), V, region ids ----
+    // ---- stage this (window, head): Q, K (content + prompt rows), [V | 1], region ids ----
     __nv_bfloat16 extra[4];
-    for (int n = tid; n < kN; n += kRows) {
+    float qn2[2];
+    float kmax2 = 0.f;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int n = t * kRows + tid;
       __nv_bfloat16 row[DH];
       load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + n) * p.ldq + head * DH, row);
+      qn2[t] = sumsq<DH>(row);
       const int id_ = n % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
@@ -191,6 +248,7 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
       const size_t off = content ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
       __nv_bfloat16 row[DH];
       load_row<DH>((const __nv_bfloat16*)(content ? p.k : p.kp) + off, row);
+      kmax2 = fmaxf(kmax2, sumsq<DH>(row));
       const int jd = j % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
@@ -201,7 +259,7 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
       for (int dc = 0; dc < NDC; ++dc) {
         __align__(16) __nv_bfloat16 tmp[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) tmp[e] = (dc * 8 + e < DH) ? row[dc * 8 + e] : zero;
+        for (int e = 0; e < 8; ++e) tmp[e] = (dc * 8 + e < DH) ? row[dc * 8 + e < DH ? dc * 8 + e : 0] : (dc * 8 + e == DH ? one : zero);
         *reinterpret_cast<uint4*>(Vs + (j >> 3) * (NDC * 128) + dc * 128 + (j & 7) * 16) =
             *reinterpret_cast<const uint4*>(tmp);
       }
@@ -209,94 +267,119 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
     if (MASKED)
       for (int i = tid; i < kN / 4; i += kRows)
         reinterpret_cast<uint32_t*>(ids_s)[i] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[i];
+    kmax2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(kmax2)));   // non-negative floats order as uints
+    if (lane == 0) kmax_s[warp] = __float_as_uint(kmax2);
     fence_proxy_async_smem();
     __syncthreads();
+    if (MASKED) {
+      // PRMT selectors: word w of row-id slot s covers keys 4w..4w+3 = packed pairs 2w (low half) and 2w+1 (high half);
+      // a kept bf16 takes its own bytes (nibbles 1,0 / 3,2), a masked one the bytes of the (e0,e0) operand (5,4 / 7,6)
+      for (int i = tid; i < kIds * (kN / 4); i += kRows) {
+        const int s = i / (kN / 4), w = i - s * (kN / 4);
+        const uint32_t idw = reinterpret_cast<const uint32_t*>(ids_s)[w];
+        uint32_t sel = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const bool keep = id_slot((idw >> (8 * e)) & 0xffu) == s;
+          const uint32_t nib = (e & 1) ? (keep ? 0x32u : 0x76u) : (keep ? 0x10u : 0x54u);
+          sel |= nib << (((e & 1) ? 8 : 0) + ((e >> 1) ? 16 : 0));
+        }
+        sel_s[i] = sel;
+      }
+    }
+    const float kmax = sqrtf(__uint_as_float(max(max(kmax_s[0], kmax_s[1]), max(kmax_s[2], kmax_s[3]))));
+    // stabiliser: upper bound of the row's logits; the row maximum itself is >= max_j bias - |q| max|k|, so
+    // `gap` bounds how far below the stabiliser the largest exponent argument can lie
+    float mb_t[2];
+    bool loose = false;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const float qk = sqrtf(qn2[t]) * kmax, rb = rowb_s[t * kRows + tid];
+      mb_t[t] = c2 * 1.01f * (qk + fmaxf(rb, 0.f));
+      loose |= (mb_t[t] - c2 * (rb - qk)) > 2.f * kMaxBound;
+    }
+    // (the __syncthreads_or also orders the selector table writes before their first use)
+    const bool exact = __syncthreads_or(loose) != 0;
 
     for (int mt = 0; mt < 2; ++mt) {
       const int rown = mt * kRows + tid;
       const uint32_t rid = MASKED ? ids_s[rown] : 0;
-      float m_run = -1e30f, l_run = 0.f;
-      float o_run[DHP];
+      float mb = mb_t[mt];
+      if (exact) {
+        // rare path: exact row maximum of the masked logits (masked entries count as 0, as in the reference)
+        float mx = -1e30f;
+        for (int kb = 0; kb < n_kb; ++kb) {
+          const int nk = kb < 2 ? 128 : p.I;
+          if (tid == 0) issue_s(mt, kb);
+          __syncwarp();
+          mbar_wait(&bar, phase);
+          phase ^= 1;
+          tc_fence_after();
+          const bool do_mask = MASKED && kb < 2;
+          for (int c = 0; c < nk / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(trow + c * 32, r);
+            tmem_wait_ld();
 #pragma unroll
-      for (int d = 0; d < DHP; ++d) o_run[d] = 0.f;
+            for (int e = 0; e < 32; ++e) {
+              float s = __uint_as_float(r[e]);
+              if (do_mask && ids_s[kb * 128 + c * 32 + e] != rid) s = 0.f;
+              mx = fmaxf(mx, s);
+            }
+          }
+          tc_fence_before();
+          __syncthreads();
+        }
+        mb = mx * c2;
+      }
+      const float e0 = fast_exp2(-mb);                           // weight of every masked (zeroed) logit
+      const uint32_t e0pair = pack_bf16(e0, e0);
+      const uint32_t* selrow = sel_s + id_slot(rid) * (kN / 4);
+      float o_run[DH + 1];
+#pragma unroll
+      for (int d = 0; d <= DH; ++d) o_run[d] = 0.f;
 
       for (int kb = 0; kb < n_kb; ++kb) {
         const int nk = kb < 2 ? 128 : p.I;
-        // ---- S = Q'.K'^T ----
-        if (tid == 0) {
-          tc_fence_after();
-          const uint32_t idesc = kb < 2 ? idescS128 : idescSP;
-#pragma unroll
-          for (int ks = 0; ks < KS; ++ks) {
-            const uint64_t da = make_smem_desc(smem_u32(Qs) + ks * 2 * (kN * 16) + mt * (kRows * 16), kN * 16, 128);
-            const uint64_t db = make_smem_desc(smem_u32(Ks) + ks * 2 * (NKT * 16) + kb * (128 * 16), NKT * 16, 128);
-            mma_ss(tmem, da, db, idesc, ks > 0);
-          }
-          const uint64_t da = make_smem_desc(smem_u32(Qa) + mt * (kRows * 16), kN * 16, 128);
-          const uint64_t db = make_smem_desc(smem_u32(Ka) + kb * (128 * 16), NKT * 16, 128);
-          mma_ss(tmem, da, db, idesc, 1);
-          mma_commit(&bar);
-        }
+        if (tid == 0) issue_s(mt, kb);
         __syncwarp();
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
 
-        // ---- pass 1: row max of the masked logits ----
+        // ---- P = exp2(S*c2 - mb), packed bf16 back into TMEM ----
         const bool do_mask = MASKED && kb < 2;
-        float mx = -1e30f;
         for (int c = 0; c < nk / 32; ++c) {
           uint32_t r[32];
           tmem_ld32(trow + c * 32, r);
           tmem_wait_ld();
-          const uint32_t* idw = reinterpret_cast<const uint32_t*>(ids_s + kb * 128 + c * 32);
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t w = do_mask ? idw[g] : 0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float s = __uint_as_float(r[g * 4 + e]);
-              if (do_mask && ((w >> (8 * e)) & 0xffu) != rid) s = 0.f;
-              mx = fmaxf(mx, s);
-            }
-          }
-        }
-        const float m_new = fmaxf(m_run, mx);
-        const float mb = m_new * c2;
-        const float e0 = fast_exp2(-mb);                         // weight of every masked (zeroed) logit
-        // ---- pass 2: P = exp2(logit - max), packed bf16 back into TMEM ----
-        float sum = 0.f;
-        for (int c = 0; c < nk / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld32(trow + c * 32, r);
-          tmem_wait_ld();
-          const uint32_t* idw = reinterpret_cast<const uint32_t*>(ids_s + kb * 128 + c * 32);
           uint32_t pk[16];
 #pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const uint32_t w = do_mask ? idw[g] : 0;
-            float pv[4];
+          for (int g = 0; g < 16; ++g) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * g]), c2, -mb));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * g + 1]), c2, -mb));
+            pk[g] = pack_bf16(p0, p1);
+          }
+          if (do_mask) {
+            const uint4* sp = reinterpret_cast<const uint4*>(selrow + kb * 32 + c * 8);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float s = __uint_as_float(r[g * 4 + e]);
-              float pe = fast_exp2(fmaf(s, c2, -mb));
-              if (do_mask && ((w >> (8 * e)) & 0xffu) != rid) pe = e0;
-              pv[e] = pe;
-              sum += pe;
+            for (int h = 0; h < 2; ++h) {
+              const uint4 s4 = sp[h];
+              const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+              for (int w = 0; w < 4; ++w) {
+                pk[h * 8 + w * 2] = prmt(pk[h * 8 + w * 2], e0pair, sw[w]);
+                pk[h * 8 + w * 2 + 1] = prmt(pk[h * 8 + w * 2 + 1], e0pair, sw[w] >> 16);
+              }
             }
-            pk[g * 2] = pack_bf16(pv[0], pv[1]);
-            pk[g * 2 + 1] = pack_bf16(pv[2], pv[3]);
           }
           tmem_st16(trow + c * 16, pk);
         }
-        const float alpha = fast_exp2((m_run - m_new) * c2);
-        l_run = l_run * alpha + sum;
-        m_run = m_new;
         tmem_wait_st();
         tc_fence_before();
         __syncthreads();
 
-        // ---- O_blk = P.V ----
+        // ---- O_blk = P.[V | 1] ----
         if (tid == 0) {
           tc_fence_after();
           for (int t = 0; t < nk / 16; ++t) {
@@ -315,13 +398,15 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
           tmem_ld16(trow + kOCol + dq * 16, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int d = 0; d < 16; ++d) o_run[dq * 16 + d] = fmaf(o_run[dq * 16 + d], alpha, __uint_as_float(o[d]));
+          for (int d = 0; d < 16; ++d)
+            if (dq * 16 + d <= DH) o_run[dq * 16 + d] += __uint_as_float(o[d]);
         }
         tc_fence_before();
         __syncthreads();   // everyone has drained O / P before the next S MMA overwrites the columns
       }
 
       // ---- epilogue: normalise, write bf16 output row slice and log-sum-exp ----
+      const float l_run = o_run[DH];
       const float inv = 1.f / l_run;
       __nv_bfloat16* og = (__nv_bfloat16*)p.out + ((size_t)bw * kN + rown) * p.C + head * DH;
       if constexpr (DH % 4 == 0) {
@@ -336,7 +421,7 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
 #pragma unroll
         for (int d = 0; d < DH; ++d) og[d] = __float2bfloat16(o_run[d] * inv);
       }
-      p.lse[((size_t)bw * p.heads + head) * kN + rown] = m_run * p.scale + __logf(l_run);
+      p.lse[((size_t)bw * p.heads + head) * kN + rown] = (mb + __log2f(l_run)) * 0.6931471805599453f;
     }
   }
   tc_fence_before();
@@ -346,12 +431,12 @@ __global__ void __launch_bounds__(kRows, 4) attn_fwd_tc_kernel(AttnParams p) {
 
 template <int DH>
 int launch_tc(const AttnParams& p, cudaStream_t st) {
-  constexpr int DHP = Cfg<DH>::DHP;
-  constexpr int KS = (DH + 4 + 15) / 16;
+  constexpr int DHP = Cfg<DH>::DHP, KS = Cfg<DH>::KS;
   const int NKT = kN + p.I;
-  const TcSmem L = tc_layout(KS, DHP, NKT);
+  const TcSmem L = tc_layout(KS, DHP, NKT, p.ids != nullptr);
   const size_t smem = L.total;
-  int grid = 148 * 4;
+  const int per_sm = (int)((227 * 1024) / (smem + 1024));
+  int grid = 148 * (per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm));
   grid -= grid % p.heads;
   const int need = p.B * p.P * p.heads;
   if (grid > need) grid = need;
@@ -372,7 +457,7 @@ bool attn_tc_supported(const AttnParams& p, int dtype) {
   if (p.I % 32 != 0 || p.I > 128) return false;                  // prompt block = one MMA of N = I, read in 32-column chunks
   const int dh = p.C / p.heads;
   if (!(dh == 12 || dh == 24 || dh == 48 || dh == 6 || dh == 3)) return false;
-  const TcSmem L = tc_layout((dh + 4 + 15) / 16, (dh + 15) / 16 * 16, kN + p.I);
+  const TcSmem L = tc_layout((dh + 4 + 15) / 16, (dh + 1 + 15) / 16 * 16, kN + p.I, true);
   return L.total <= 200 * 1024;
 }
 

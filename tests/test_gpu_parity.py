@@ -77,11 +77,11 @@ def test_partition_full_size_round_trip(dims, C, B, dtype):
         assert torch.equal(tok, flat[:, :, idx].reshape(B, C, g.P, g.N).permute(0, 2, 3, 1))
 
 
-def _attn_inputs(B, P, ws, C, heads, I, masked, seed, dtype=torch.float64):
+def _attn_inputs(B, P, ws, C, heads, I, masked, seed, dtype=torch.float64, qk_gain=1.0):
     gen = torch.Generator().manual_seed(seed)
     N = ws[0] * ws[1] * ws[2]
     r = lambda *s: torch.randn(*s, generator=gen, dtype=torch.float64)
-    q, k, v = r(B, P, N, C), r(B, P, N, C), r(B, P, N, C)
+    q, k, v = qk_gain * r(B, P, N, C), qk_gain * r(B, P, N, C), r(B, P, N, C)
     kp, vp = (r(B, I, C), r(B, I, C)) if I else (None, None)
     th, tw, td = 0.5 * r(heads, ws[0], ws[0]), 0.5 * r(heads, ws[1], ws[1]), 0.5 * r(heads, ws[2], ws[2])
     tok = 0.5 * r(heads, I) if I else None
@@ -158,6 +158,24 @@ def test_attention_tcgen05_vs_oracle(case):
     for n, t, g in zip(["q", "k", "v", "kp", "vp", "th", "tw", "td", "tok"], dev, ref_grads):
         if t is not None:
             assert rel_linf(t.grad, g) < RTOL_BF16, n
+
+
+@pytest.mark.parametrize("case", [(1, 2, (8, 8, 4), 48, 4, 64, True), (1, 2, (8, 8, 4), 48, 4, 64, False),
+                                  (1, 1, (8, 8, 4), 96, 4, 32, True)])
+def test_attention_tcgen05_large_logits_exact_max_path(case):
+    """Logits far beyond the range where the norm-bound stabiliser is safe (|q||k|*scale ~ 100): the tcgen05
+    forward must switch to its exact-row-max sweep and still match the fp32-math kernel / oracle."""
+    B, P, ws, C, heads, I, masked = case
+    ten, ids, go = _attn_inputs(B, P, ws, C, heads, I, masked, seed=11, qk_gain=5.0)
+    scale = (C // heads) ** -0.5
+    dtype = torch.bfloat16
+    ten_r = [None if t is None else (t.to(dtype).double() if i < 5 else t.float().double()) for i, t in enumerate(ten)]
+    ref_out, _ = _oracle_attn(ten_r, ids, go.to(dtype).double(), heads, ws, scale)
+    dev = [None if t is None else (t.to(DEV, dtype) if i < 5 else t.to(DEV, torch.float32)) for i, t in enumerate(ten)]
+    ids_d = None if ids is None else ids.to(DEV)
+    out = PF.prompted_window_attention(*dev, ids_d, heads, ws, scale, PF.IMPL_TC)
+    assert torch.isfinite(out.float()).all()
+    assert rel_linf(out, ref_out) < RTOL_BF16
 
 
 def _make_block(meta, sd, dtype=torch.float32):

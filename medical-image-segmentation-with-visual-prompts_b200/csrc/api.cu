@@ -1,4 +1,6 @@
 // C-ABI entry points of the attention path: argument validation + dispatch.
+#include <stdlib.h>
+
 #include "attn.cuh"
 
 namespace pwa {
@@ -23,6 +25,8 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
   p.ldq = s->ld_qkv > 0 ? s->ld_qkv : s->C;
   p.ldp = s->ld_p > 0 ? s->ld_p : s->C;
   PWA_CHECK_ARG(p.ldq >= s->C && p.ldp >= s->C, "%s: row strides must be >= C", who);
+  static const int dbg = getenv("PWA_TIMELINE") != nullptr;
+  p.debug = dbg;
   return PWA_OK;
 }
 

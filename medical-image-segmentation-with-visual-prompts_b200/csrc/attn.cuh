@@ -17,6 +17,7 @@ struct AttnParams {
   int ldq, ldp;      // row strides (elements) of q/k/v (+ dq/dk/dv) and of kp/vp; out/dout/dkp/dvp use C
   int wh, ww, wd;
   float scale;
+  int debug;         // PWA_TIMELINE=1: CTA 0 writes clock64 stamps into the (otherwise unused) delta buffer
 };
 
 // fp32-math CUDA-core kernels (attn_f32.cu)

@@ -425,6 +425,7 @@ class _WindowAttentionPacked(torch.autograd.Function):
                                        _ptr(dth), _ptr(dtw), _ptr(dtd), _ptr(dtok), _ptr(delta), C.byref(s),
                                        _dtype_code(qkv), impl, _stream(qkv))
         _lib.check(rc, "pwa_attn_bwd")
+        _WindowAttentionPacked.last_delta = delta
         dkvp = None
         if I:
             dkvp = torch.cat([dkvp32[0], dkvp32[1]], dim=-1).to(qkv.dtype)          # [B,I,2C]

@@ -20,7 +20,7 @@ for _ in range(2):
     out.backward(torch.randn_like(out))
 torch.cuda.synchronize()
 d = PF._WindowAttentionPacked.last_delta.reshape(-1).view(torch.int64).cpu()
-for name, base in (("tid0", 0), ("tid128(issuer)", 2048), ("tid255", 4096)):
+for name, base in (("compute tid0", 0), ("S issuer", 2048), ("V issuer", 4096), ("producer", 6144)):
     ev = [(int(d[base + 2 * i]), int(d[base + 2 * i + 1])) for i in range(1000)]
     ev = [e for e in ev if 0 < e[1] < 200]
     # second window of this CTA: from the 2nd tag==1 to the 3rd

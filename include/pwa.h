@@ -91,6 +91,18 @@ int pwa_reverse(const void* tokens, void* x, int B, int C, const pwa_geom* g, in
 int pwa_reverse_add(const void* tokens_a, const void* tokens_b, void* x, int B, int C, const pwa_geom* g,
                     int use_crop_lo, int dtype, void* stream);
 
+/* Row gather between channels-last arrangements: dst [B][rows_dst][C] <- src [B][rows_src][C] with
+ * dst[b][j][:] = map[j] >= 0 ? src_a[b][map[j]][:] (+ src_b[b][map[j]][:] when src_b != NULL) : 0.
+ * map: int32 [rows_dst] on the DEVICE, shared by all samples.  With maps composed on the host from
+ * pwa_index_map() this is, without leaving the token layout, any chain of
+ * window_reverse -> roll back -> crop -> pad -> roll -> window_partition between two blocks of a
+ * ConsecutiveSwinBlocks pair (swin_block.py:66-71, 228-253, 150-214), the 2x2x2 strided slices + cat of
+ * PatchMerging (down.py:21-47), and the partition of a channels-last feature map (the strides
+ * down.py:48-53 leaves).  src_b fuses the block's last residual add (swin_block.py:227; fp32 sum, rounded once).
+ * Every map is injective, so the adjoint is the same call with the inverse map. */
+int pwa_gather_rows(const void* src_a, const void* src_b, void* dst, const int32_t* map, int B,
+                    int64_t rows_src, int64_t rows_dst, int C, int dtype, void* stream);
+
 /* ---- (b) fused prompted window attention, forward -------------------------------------------- */
 
 typedef struct pwa_attn_shape {

@@ -7,9 +7,11 @@ include/pwa.h) and fails loudly if it is not built.  The directory name contains
 from . import _lib
 from .geometry import Geometry, get_geometry
 from . import functional
+from . import graphs
+from .graphs import GraphedStep
 from .modules import (ConsecutiveSwinBlocks, SwinTransformerBlock, PatchMerging, WindowAttention, RelativePE,
                       BiasTables, window_partition, window_reverse, get_attn_mask)
 
 __all__ = ['ConsecutiveSwinBlocks', 'SwinTransformerBlock', 'PatchMerging', 'WindowAttention', 'RelativePE',
            'BiasTables', 'window_partition', 'window_reverse', 'get_attn_mask', 'Geometry', 'get_geometry',
-           'functional']
+           'functional', 'graphs', 'GraphedStep']

@@ -52,6 +52,8 @@ def _load():
     lib.pwa_reverse.argtypes = [vp, vp, i32, i32, gp, i32, i32, vp]
     lib.pwa_reverse_add.argtypes = [vp, vp, vp, i32, i32, gp, i32, i32, vp]
     lib.pwa_reverse_add.restype = i32
+    lib.pwa_gather_rows.argtypes = [vp, vp, vp, vp, i32, C.c_int64, C.c_int64, i32, i32, vp]
+    lib.pwa_gather_rows.restype = i32
     lib.pwa_attn_tc_supported.argtypes = [sp, i32]
     lib.pwa_attn_fwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, sp, i32, i32, vp]
     lib.pwa_attn_bwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, vp] + [vp] * 3 + [f32p] * 7 + [sp, i32, i32, vp]
@@ -72,7 +74,7 @@ def _load():
 lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
-                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
+                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
                     "pwa_ln_fwd", "pwa_ln_bwd", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 

@@ -167,6 +167,47 @@ def reverse_tokens(tok: torch.Tensor, geom: Geometry) -> torch.Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# row gather between channels-last arrangements (csrc/gather.cu)
+# ------------------------------------------------------------------------------------------------
+def _gather_rows_raw(a: torch.Tensor, b: Optional[torch.Tensor], idx: torch.Tensor, rows_src: int, rows_dst: int):
+    B, Cc = a.shape[0], a.shape[-1]
+    out = torch.empty((B, rows_dst, Cc), dtype=a.dtype, device=a.device)
+    nbytes = ((2 if b is None else 3) * min(rows_src, rows_dst) * B * Cc) * a.element_size()
+    with torch.cuda.device(a.device), _timed("gather_rows", 1, float(nbytes), a):
+        rc = _lib.lib.pwa_gather_rows(_ptr(a), _ptr(b), _ptr(out), _ptr(idx), B, rows_src, rows_dst, Cc, _dtype_code(a),
+                                      _stream(a))
+    _lib.check(rc, "pwa_gather_rows")
+    return out
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, rowmap):
+        fwd, bwd = rowmap.on(a.device)
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        ctx.rowmap, ctx.has_b, ctx.in_shape = rowmap, b is not None, a.shape
+        ctx.save_for_backward(bwd)
+        return _gather_rows_raw(a, b, fwd, rowmap.rows_src, rowmap.rows_dst)
+
+    @staticmethod
+    def backward(ctx, g):
+        (bwd,) = ctx.saved_tensors
+        rm = ctx.rowmap
+        d = _gather_rows_raw(g.contiguous(), None, bwd, rm.rows_dst, rm.rows_src).view(ctx.in_shape)
+        return d, (d if ctx.has_b else None), None
+
+
+def gather_rows(a: torch.Tensor, b: Optional[torch.Tensor], rowmap) -> torch.Tensor:
+    """out[B, rows_dst, C] with out[:, j] = a[:, map[j]] (+ b[:, map[j]]) or 0 where map[j] < 0.  a (and b) hold
+    rowmap.rows_src rows of C contiguous elements per sample (any leading shape)."""
+    _require_cuda(a, b)
+    if a.numel() != a.shape[0] * rowmap.rows_src * a.shape[-1] or (b is not None and (b.shape != a.shape or b.dtype != a.dtype)):
+        raise ValueError(f"gather_rows: source {tuple(a.shape)} does not hold {rowmap.rows_src} rows per sample")
+    return _GatherRows.apply(a, b, rowmap)
+
+
+# ------------------------------------------------------------------------------------------------
 # (b)/(c) fused prompted window attention
 # ------------------------------------------------------------------------------------------------
 IMPL_AUTO, IMPL_F32, IMPL_TC = 0, 1, 2
@@ -458,8 +499,10 @@ class _MultiLinear(torch.autograd.Function):
     """y = x @ cat(weights)^T (+ bias): several nn.Linear weights that share an input, as ONE GEMM."""
 
     @staticmethod
-    def forward(ctx, x, bias, *weights):
-        w = (weights[0] if len(weights) == 1 else torch.cat(weights, dim=0)).detach().to(x.dtype)
+    def forward(ctx, x, bias, lowp, *weights):
+        # `lowp`: the same weights already concatenated and cast to x.dtype (one cat + one cast per block instead
+        # of two kernels per Linear); the fp32 master weights stay the autograd inputs
+        w = lowp if lowp is not None else (weights[0] if len(weights) == 1 else torch.cat(weights, dim=0)).detach().to(x.dtype)
         x2 = x.reshape(-1, x.shape[-1])
         if bias is not None:
             y = torch.addmm(bias.detach().to(x.dtype), x2, w.t())
@@ -478,15 +521,15 @@ class _MultiLinear(torch.autograd.Function):
         dx = torch.mm(dy2, w).reshape(xshape) if ctx.needs_input_grad[0] else None
         db = dy2.sum(dim=0, dtype=torch.float32).to(bdt) if bdt is not None and ctx.needs_input_grad[1] else None
         dws = [None] * len(rows)
-        if any(ctx.needs_input_grad[2:]):
+        if any(ctx.needs_input_grad[3:]):
             dw = _mm_f32(dy2.t(), x2)
             o = 0
             for i, r in enumerate(rows):
-                if ctx.needs_input_grad[2 + i]:
+                if ctx.needs_input_grad[3 + i]:
                     dws[i] = dw[o:o + r].to(wdts[i])
                 o += r
-        return (dx, db, *dws)
+        return (dx, db, None, *dws)
 
 
-def multi_linear(x, bias, *weights):
-    return _MultiLinear.apply(x, bias, *weights)
+def multi_linear(x, bias, *weights, lowp=None):
+    return _MultiLinear.apply(x, bias, lowp, *weights)

@@ -1,0 +1,73 @@
+"""Whole-step CUDA-graph capture for training steps built on the pwa kernels.
+
+One forward+backward of the prompted Swin encoder is ~450 kernel launches (ours + cuBLAS + a few torch
+elementwise ops), most of them 3-50 us long: launched eagerly from Python the step is bound by the host, not
+by the GPU.  Every pwa C-ABI entry point launches on the caller's stream, allocates nothing and never
+synchronises (include/pwa.h), so a whole step -- forward, loss, backward -- can be captured ONCE into a CUDA
+graph and replayed with a single launch.  This is the "streams and graphs" replacement for a tracing compiler:
+the Python module code still defines the step; the graph only removes the per-launch host cost.
+
+    step = GraphedStep(lambda x: encoder_step(model, prompts, x), [x_example], params)
+    loss = step(x_batch)          # copies x_batch into the static input, replays, returns the static loss tensor
+    # parameter gradients are in p.grad (static tensors, overwritten by every replay)
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, List, Sequence
+
+import torch
+
+from .functional import KernelStats
+
+
+class GraphedStep:
+    def __init__(self, step_fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor],
+                 params: Iterable[torch.nn.Parameter], warmup: int = 3):
+        """step_fn(*inputs) must run forward AND backward and return a (scalar) loss tensor; it is called `warmup`
+        times eagerly on a side stream (lazy initialisation: cuBLAS handles, kernel attributes, cached index maps),
+        then once more under capture.  Inputs that require grad get a static .grad too (`input_grads`)."""
+        if not example_inputs or not all(t.is_cuda for t in example_inputs):
+            raise RuntimeError("GraphedStep: CUDA tensors only (pwa_b200 has no CPU path)")
+        self.params: List[torch.nn.Parameter] = [p for p in params]
+        self.static_inputs = [t.detach().clone().requires_grad_(t.requires_grad) for t in example_inputs]
+        self._step_fn = step_fn
+        # CUDA events cannot be recorded inside a capture; launches are counted during the capture pass
+        saved = (KernelStats.enabled, KernelStats.timing, KernelStats.launches)
+        KernelStats.enabled, KernelStats.timing = True, False
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self._zero()
+                    step_fn(*self.static_inputs)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._zero()
+            self.graph = torch.cuda.CUDAGraph()
+            launches0 = KernelStats.launches
+            with torch.cuda.graph(self.graph):
+                self.loss = step_fn(*self.static_inputs)
+            self.launches_per_replay = KernelStats.launches - launches0   # pwa kernels inside one replay
+        finally:
+            KernelStats.enabled, KernelStats.timing, KernelStats.launches = saved
+
+    def _zero(self):
+        for p in self.params:
+            p.grad = None
+        for t in self.static_inputs:
+            t.grad = None
+
+    @property
+    def input_grads(self):
+        return [t.grad for t in self.static_inputs]
+
+    def __call__(self, *inputs: torch.Tensor) -> torch.Tensor:
+        with torch.no_grad():
+            for s, t in zip(self.static_inputs, inputs):
+                if t is not s:
+                    s.copy_(t, non_blocking=True)
+        self.graph.replay()
+        if KernelStats.enabled:
+            KernelStats.launches += self.launches_per_replay
+        return self.loss

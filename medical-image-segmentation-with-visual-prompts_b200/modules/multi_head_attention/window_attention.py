@@ -43,10 +43,11 @@ class WindowAttention(nn.Module):
         self.impl = PF.IMPL_AUTO
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias: Optional[BiasTables] = None,
-                mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None):
+                mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None, lowp: Optional[dict] = None):
         """q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
         appended to the keys/values of every window; pos_bias: BiasTables; mask: uint8 region ids [P,N]
-        (mask[p,i,j] = ids[p,i]==ids[p,j]) or None.  Returns [B,P,N,C]."""
+        (mask[p,i,j] = ids[p,i]==ids[p,j]) or None; lowp: optional {'qkv','kv','proj'} weights already cast to the
+        compute dtype (SwinTransformerBlock packs them once per forward).  Returns [B,P,N,C]."""
         if pos_bias is None or not isinstance(pos_bias, BiasTables):
             raise NotImplementedError("WindowAttention on the fused kernels takes the compact BiasTables form of the "
                                       "position bias (RelativePE.tables), not a dense [1,1,h,N',N'] tensor")
@@ -55,8 +56,10 @@ class WindowAttention(nn.Module):
         if q is k and k is v:
             # self-attention (the only way the block calls it): ONE fused [C -> 3C] projection GEMM; the kernels
             # read q|k|v as column blocks of its output (row stride 3C), prompt K/V likewise from [C -> 2C]
-            qkv = PF.multi_linear(q, None, self.to_q.weight, self.to_k.weight, self.to_v.weight)
-            kvp = PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight) if prompts is not None else None
+            lp = lowp or {}
+            qkv = PF.multi_linear(q, None, self.to_q.weight, self.to_k.weight, self.to_v.weight, lowp=lp.get('qkv'))
+            kvp = PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight, lowp=lp.get('kv')) \
+                if prompts is not None else None
             o = PF.prompted_window_attention_packed(qkv, kvp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
                                                     self.num_heads, pos_bias.ws, self.scale, self.impl)
         else:
@@ -69,5 +72,5 @@ class WindowAttention(nn.Module):
                 vp = PF.multi_linear(prompts, None, self.to_v.weight)
             o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok,
                                              mask, self.num_heads, pos_bias.ws, self.scale, self.impl)
-        o = PF.multi_linear(o, self.proj.bias, self.proj.weight)
+        o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'))
         return self.proj_drop(o)

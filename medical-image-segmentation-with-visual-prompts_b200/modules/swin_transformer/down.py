@@ -20,7 +20,34 @@ class PatchMerging(nn.Module):
         self.reduction = nn.Linear(k * in_channels, out_channels, bias=False)
         self.merge_last_dim = merge_last_dim
 
+    def _norm_reduce(self, t):
+        from ... import functional as PF
+        t = PF.layer_norm(t, self.norm.weight, self.norm.bias, self.norm.eps)
+        return PF.multi_linear(t, None, self.reduction.weight)
+
+    def forward_tokens(self, y, m, geom):
+        """Block output tokens y + m in window order `geom` -> merged feature map.  The window reverse, the 2x2x2
+        strided slices + cat (:21-47) and the block's last residual add are ONE row gather (csrc/gather.cu)."""
+        from ... import functional as PF
+        from ...geometry import rowmap_merge
+        rm, (h2, w2, d2) = rowmap_merge(geom, bool(self.merge_last_dim))
+        b, c = y.shape[0], y.shape[-1]
+        k = 8 if self.merge_last_dim else 4
+        t = PF.gather_rows(y, m, rm).view(b, h2 * w2 * d2, k * c)
+        t = self._norm_reduce(t)
+        # same strides as the reference's final rearrange (a permuted view, :48-53)
+        return t.view(b, h2, w2, d2, -1).permute(0, 4, 1, 2, 3)
+
     def forward(self, x):
+        from ... import functional as PF
+        k = 8 if self.merge_last_dim else 4
+        if x.is_cuda and x.dim() == 5 and x.shape[1] > 1 and x.permute(0, 2, 3, 4, 1).is_contiguous() \
+                and PF.layer_norm_supported(k * x.shape[1]) and x.dtype in (torch.float32, torch.bfloat16):
+            from ...geometry import rowmap_merge_from_voxels
+            b, c = x.shape[:2]
+            rm, (h2, w2, d2) = rowmap_merge_from_voxels(tuple(int(v) for v in x.shape[2:]), bool(self.merge_last_dim))
+            t = PF.gather_rows(x.permute(0, 2, 3, 4, 1).reshape(b, -1, c), None, rm).view(b, h2 * w2 * d2, k * c)
+            return self._norm_reduce(t).view(b, h2, w2, d2, -1).permute(0, 4, 1, 2, 3)
         h, w, d = x.shape[2:]
         if h % 2 or w % 2 or d % 2:
             x = F.pad(x, (d % 2, 0, w % 2, 0, h % 2, 0))
@@ -37,7 +64,7 @@ class PatchMerging(nn.Module):
         else:
             t = F.layer_norm(t, self.norm.normalized_shape, self.norm.weight.to(dt), self.norm.bias.to(dt), self.norm.eps)
             t = F.linear(t, self.reduction.weight.to(dt))
-        return t.permute(0, 4, 1, 2, 3).contiguous()
+        return t.permute(0, 4, 1, 2, 3)
 
     def named_parameters_body(self):
         return [*self.reduction.named_parameters(), *self.norm.named_parameters()]

@@ -26,9 +26,25 @@ import torch.nn.functional as F
 import torch.utils.checkpoint as checkpoint
 
 from ... import functional as PF
-from ...geometry import get_geometry
+from ...geometry import get_geometry, rowmap_from_voxels, rowmap_regroup
 from ..multi_head_attention import BiasTables, RelativePE, WindowAttention
 from .down import PatchMerging
+
+
+def _is_channels_last(x):
+    """[B,C,H,W,D] tensor whose memory is [B,H,W,D,C]-contiguous (what PatchMerging's final rearrange leaves,
+    reference down.py:48-53)."""
+    return x.dim() == 5 and x.shape[1] > 1 and x.permute(0, 2, 3, 4, 1).is_contiguous()
+
+
+def _partition_any(x, geom):
+    """pad + roll + strided window partition -> [B,P,N,C]: a row gather for channels-last memory, the transposing
+    partition kernel (csrc/partition.cu) for the reference's channels-first layout."""
+    if _is_channels_last(x):
+        b, c = x.shape[:2]
+        rows = x.permute(0, 2, 3, 4, 1).reshape(b, -1, c)
+        return PF.gather_rows(rows, None, rowmap_from_voxels(geom)).view(b, geom.P, geom.N, c)
+    return PF.partition_tokens(x, geom)
 
 
 class ConsecutiveSwinBlocks(nn.Module):
@@ -57,10 +73,35 @@ class ConsecutiveSwinBlocks(nn.Module):
                                       out_channels=2 * hidden_channels if out_channels is None else out_channels,
                                       merge_last_dim=merge_last_dim)
 
+    def _token_pipeline_ok(self, x):
+        if not x.is_cuda or self.use_checkpoint or x.dim() != 5:
+            return False
+        # block-level hooks must keep firing: fall back to calling the blocks one by one
+        mods = list(self.swin_blocks) + ([self.merge] if self.down else [])
+        return not any(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks for m in mods)
+
     def forward(self, x, p=(None, None)):
-        for blk, prompt in zip(self.swin_blocks, p):
-            x = blk(x, prompt)
-        return self.merge(x) if self.down else x
+        if not self._token_pipeline_ok(x):
+            for blk, prompt in zip(self.swin_blocks, p):
+                x = blk(x, prompt)
+            return self.merge(x) if self.down else x
+        # Token pipeline: between the two blocks (and into PatchMerging) the feature map never leaves the
+        # channels-last token layout.  The reference's window_reverse -> roll back -> crop -> pad -> roll ->
+        # window_partition chain (:228-253 then :150-214) is ONE row gather (csrc/gather.cu) with a host-composed
+        # index map, fused with the block's last residual add.
+        blk0, blk1 = self.swin_blocks
+        g0, g1 = blk0._geometry(x.shape[2:]), blk1._geometry(x.shape[2:])
+        cdt, in_dtype = blk0._compute_dtype(x), x.dtype
+        with torch.autocast('cuda', enabled=False):
+            tok = _partition_any(x.to(cdt), g0)
+            y, m = blk0._tokens_forward(tok, p[0], g0, cdt)
+            tok = PF.gather_rows(y, m, rowmap_regroup(g0, g1)).view(x.shape[0], g1.P, g1.N, x.shape[1])
+            y, m = blk1._tokens_forward(tok, p[1], g1, cdt)
+            if self.down:
+                out = self.merge.forward_tokens(y, m, g1)
+            else:
+                out = PF.reverse_add_tokens(y, m, g1)
+        return out.to(in_dtype)
 
     def named_parameters_body(self):
         out = [kv for blk in self.swin_blocks for kv in blk.named_parameters_body()]
@@ -101,38 +142,56 @@ class SwinTransformerBlock(nn.Module):
             return torch.bfloat16
         return torch.float32
 
+    def _lowp_weights(self, cdt):
+        """The five Linear weights of the block concatenated and cast to the compute dtype with ONE cat + ONE cast
+        (instead of a cast per Linear and call); slices: qkv [3C,C], kv [2C,C], proj [C,C], mlp [C,C]."""
+        with torch.no_grad():
+            a = self.attn
+            c = self.mlp.weight.shape[0]
+            w = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight, a.proj.weight, self.mlp.weight], dim=0).to(cdt)
+        return {'qkv': w[:3 * c], 'kv': w[c:3 * c], 'proj': w[3 * c:4 * c], 'mlp': w[4 * c:]}
+
+    def _tokens_forward(self, xw, p, geom, cdt):
+        """Window tokens [B,P,N,C] (= shortcut) -> (y, m) with block output tokens = y + m  (reference :215-227);
+        the last add is left to the consumer (window reverse / regroup / PatchMerging gather fuse it)."""
+        ws = tuple(self.window_size)
+        n_prompt = 0 if p is None else p.size(1)
+        th, tw, td, tok = self.pe.tables(ws[0], ws[1], ws[2], n_prompt)
+        ids = geom.region_ids(xw.device) if geom.masked else None
+        c = xw.shape[-1]
+        lowp = self._lowp_weights(cdt)
+        if PF.layer_norm_supported(c):
+            # pwa LayerNorm kernels (csrc/ln.cu); the `+ shortcut` of :222 is fused into mlp_norm
+            tokens = PF.layer_norm(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
+            prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6) \
+                if p is not None else None
+            a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
+                          prompts=prompts, lowp=lowp)
+            y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6)
+        else:
+            nw, nb = self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt)
+            tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)
+            prompts = F.layer_norm(p.to(cdt), (c,), nw, nb, 1e-6) if p is not None else None
+            y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
+                          prompts=prompts, lowp=lowp)
+            y = y + xw
+            z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
+        m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'])
+        return y, m
+
+    def _geometry(self, dims):
+        shift_cfg = tuple(self.shift_size) if self.shift_size is not None else (0, 0, 0)
+        return get_geometry(tuple(int(d) for d in dims), tuple(self.window_size), shift_cfg)
+
     def forward_attn_mlp(self, x, p=None):
         if not x.is_cuda:
             raise RuntimeError("pwa_b200.SwinTransformerBlock runs on CUDA (sm_100a) only; there is no CPU path")
-        ws = tuple(self.window_size)
-        shift_cfg = tuple(self.shift_size) if self.shift_size is not None else (0, 0, 0)
-        geom = get_geometry(tuple(x.shape[2:]), ws, shift_cfg)
+        geom = self._geometry(x.shape[2:])
         cdt = self._compute_dtype(x)
         in_dtype = x.dtype
-        n_prompt = 0 if p is None else p.size(1)
-        th, tw, td, tok = self.pe.tables(ws[0], ws[1], ws[2], n_prompt)
-        ids = geom.region_ids(x.device) if geom.masked else None
-
         with torch.autocast('cuda', enabled=False):
-            xw = PF.partition_tokens(x.to(cdt), geom)                       # [B,P,N,C] = shortcut
-            c = xw.shape[-1]
-            if PF.layer_norm_supported(c):
-                # pwa LayerNorm kernels (csrc/ln.cu); the `+ shortcut` of :222 is fused into mlp_norm
-                tokens = PF.layer_norm(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
-                prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6) \
-                    if p is not None else None
-                a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                              prompts=prompts)
-                y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6)
-            else:
-                nw, nb = self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt)
-                tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)
-                prompts = F.layer_norm(p.to(cdt), (c,), nw, nb, 1e-6) if p is not None else None
-                y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                              prompts=prompts)
-                y = y + xw
-                z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
-            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight)
+            xw = _partition_any(x.to(cdt), geom)                            # [B,P,N,C] = shortcut
+            y, m = self._tokens_forward(xw, p, geom, cdt)
             out = PF.reverse_add_tokens(y, m, geom)                         # reverse(y + mlp(LN2(y))) -> [B,C,H,W,D]
         return out.to(in_dtype)
 

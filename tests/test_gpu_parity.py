@@ -345,3 +345,97 @@ def test_bias_tables_kernel_vs_reference_golden():
     sum((o * g.double()).sum() for o, g in zip(out_c, gs)).backward()
     for (n, pg), (_, pc) in zip(pe_gpu.named_parameters(), pe_cpu.named_parameters()):
         assert rel_linf(pg.grad, pc.grad) < 1e-5, n
+
+
+# --------------------------------------------------------------------------------------------------
+# token pipeline: row gather kernel + pair-level regroup / merge
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("C", [3, 7, 12, 48, 192])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("add", [False, True])
+def test_gather_rows_kernel_bit_exact(C, dtype, add):
+    from pwa_b200.geometry import RowMap
+    rs = np.random.RandomState(C)
+    rows_src, rows_dst, B = 1000, 1357, 3
+    fwd = rs.permutation(rows_dst).astype(np.int64)
+    fwd = np.where(fwd < rows_src, fwd, -1)                       # injective, with holes
+    bwd = np.full(rows_src, -1, dtype=np.int64)
+    bwd[fwd[fwd >= 0]] = np.nonzero(fwd >= 0)[0]
+    rm = RowMap(fwd, bwd)
+    gen = torch.Generator().manual_seed(2)
+    a = torch.randn(B, rows_src, C, generator=gen).to(dtype)
+    b = torch.randn(B, rows_src, C, generator=gen).to(dtype) if add else None
+    src = a if b is None else (a.float() + b.float()).to(dtype)   # fp32 sum, rounded once
+    exp = torch.zeros(B, rows_dst, C, dtype=dtype)
+    ok = torch.from_numpy(fwd >= 0)
+    exp[:, ok] = src[:, torch.from_numpy(fwd[fwd >= 0])]
+    ad = a.to(DEV).requires_grad_(True)
+    bd = b.to(DEV).requires_grad_(True) if add else None
+    got = PF.gather_rows(ad, bd, rm)
+    assert torch.equal(got.cpu(), exp)
+    g = torch.randn(B, rows_dst, C, generator=gen).to(dtype)
+    got.backward(g.to(DEV))
+    exp_g = torch.zeros(B, rows_src, C, dtype=dtype)
+    okb = torch.from_numpy(bwd >= 0)
+    exp_g[:, okb] = g[:, torch.from_numpy(bwd[bwd >= 0])]
+    assert torch.equal(ad.grad.cpu(), exp_g)
+    if add:
+        assert torch.equal(bd.grad.cpu(), exp_g)
+
+
+@pytest.mark.parametrize("dims,C,B", [((48, 48, 48), 48, 4), ((12, 12, 24), 192, 2)])
+def test_regroup_full_size_matches_reverse_then_partition(dims, C, B):
+    """BASELINE-size: the one-kernel regroup equals the transposing reverse kernel followed by the partition kernel."""
+    from pwa_b200.geometry import rowmap_regroup
+    ws = (8, 8, 4)
+    g0, g1 = pwa_b200.get_geometry(dims, ws, (0, 0, 0)), pwa_b200.get_geometry(dims, ws, (4, 4, 2))
+    gen = torch.Generator().manual_seed(11)
+    y = torch.randn(B, g0.P, g0.N, C, generator=gen).bfloat16().to(DEV)
+    m = torch.randn(B, g0.P, g0.N, C, generator=gen).bfloat16().to(DEV)
+    exp = PF._partition_raw(PF.reverse_add_tokens(y, m, g0), g1, 0)
+    got = PF.gather_rows(y, m, rowmap_regroup(g0, g1)).view_as(exp)
+    assert torch.equal(got, exp)
+
+
+def _pair_case(tag, d, mld, down=True):
+    sd = {k[len(tag) + 4:]: torch.from_numpy(v) for k, v in d.items() if k.startswith(tag + ".sd.")}
+    if not down:
+        sd = {k: v for k, v in sd.items() if not k.startswith("merge.")}
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=12, num_heads=2, pos_bias_embed_dim=16, max_prompts=1,
+                                          tokens_per_prompt=8, window_size=(4, 4, 2), down=down, merge_last_dim=mld)
+    pair.load_state_dict(sd)
+    return pair.to(DEV)
+
+
+@pytest.mark.parametrize("down", [True, False])
+def test_pair_token_pipeline_equals_block_by_block(down):
+    """The pair-level token pipeline (regroup / merge gathers) must reproduce the block-by-block path (partition ->
+    block -> reverse per block, then PatchMerging), for channels-first AND channels-last input memory."""
+    from tests.util import load_npz
+    d = load_npz("pair_merge")
+    for tag, mld in (("mld1", True), ("mld0", False)):
+        pair = _pair_case(tag, d, mld, down)
+        x0 = torch.from_numpy(d[f"{tag}.x"]).to(DEV)
+        p0 = torch.from_numpy(d[f"{tag}.p0"]).to(DEV)
+        p1 = torch.from_numpy(d[f"{tag}.p1"]).to(DEV)
+        res = []
+        for mode in ("pipeline", "pipeline_cl", "blocks"):
+            x = x0.clone()
+            if mode == "pipeline_cl":
+                x = x.permute(0, 2, 3, 4, 1).contiguous().permute(0, 4, 1, 2, 3)
+            x.requires_grad_(True)
+            h = pair.swin_blocks[0].register_forward_hook(lambda *a: None) if mode == "blocks" else None
+            for prm in pair.parameters():
+                prm.grad = None
+            y = pair(x, (p0, p1))
+            if h is not None:
+                h.remove()
+            y.square().sum().backward()
+            res.append((y.detach().clone(), x.grad.clone(), pair.swin_blocks[0].attn.to_q.weight.grad.clone()))
+        if down:
+            assert rel_linf(res[0][0], torch.from_numpy(d[f"{tag}.out"])) < RTOL_F32
+            assert res[0][0].permute(0, 2, 3, 4, 1).is_contiguous()          # the reference returns a permuted view
+        for other in res[1:]:
+            assert torch.equal(res[0][0], other[0])
+            for a, b in zip(res[0][1:], other[1:]):
+                assert rel_linf(a, b) < 1e-5

@@ -38,9 +38,12 @@ using namespace tc;
 namespace {
 
 constexpr int kN = 256;
-constexpr int kThreadsB = 512;
-constexpr int kCompute = 256;     // compute threads (warps 0-7)
-constexpr int kProd = 96;         // staging threads (warps 13-15)
+constexpr int kThreadsB = 768;
+constexpr int kCompute = 256;     // compute threads per group: group 0 = warps 0-7 (even units), group 1 = warps 8-15 (odd units)
+constexpr int kGroups = 2;
+constexpr int kIssue0 = kGroups * 8;   // first MMA-issuer warp (S, V, K, A, Q)
+constexpr int kProd0 = kIssue0 + 5;    // first staging warp
+constexpr int kProd = 96;         // staging threads (3 warps)
 constexpr int kIds = 28;          // region ids 0..26 and 100 (-> 27), see pwa_region_ids
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -272,15 +275,22 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
 
   long long* tl = reinterpret_cast<long long*>(p.delta);
   int tli = 0;
-  const bool rec = p.debug && blockIdx.x == 0 && (tid == 0 || tid == 256 || tid == 288 || tid == 416);
-  const int tlb = tid == 0 ? 0 : (tid == 256 ? 2048 : (tid == 288 ? 4096 : 6144));
+  const bool rec = p.debug && blockIdx.x == 0 &&
+                   (tid == 0 || tid == kIssue0 * 32 || tid == (kIssue0 + 1) * 32 || tid == kProd0 * 32 || tid == 256 ||
+                    tid == (kIssue0 + 4) * 32);
+  const int tlb = tid == 0 ? 0 : (tid == kIssue0 * 32 ? 2048 : (tid == (kIssue0 + 1) * 32 ? 4096 : (tid == 256 ? 8192 :
+                  (tid == (kIssue0 + 4) * 32 ? 10240 : 6144))));
 #define STAMP(tag) do { if (rec && tli < 1000) { tl[tlb + 2 * tli] = clock64(); tl[tlb + 2 * tli + 1] = (tag); ++tli; } } while (0)
 
-  if (warp < 8) {
+  if (warp < kIssue0) {
     // =============================================================================================
-    // compute warps
+    // compute warps: two groups of 8 warps ping-pong over the units (group 0: even units = first 64-row half of a
+    // query tile, group 1: odd units + every accumulator drain), so that the waits / TMEM round trips / proxy
+    // fences of one group hide behind the exponentials of the other and 4 warps per scheduler feed the MUFU pipe
     // =============================================================================================
-    const int wg = tid >> 7;
+    const int grp = warp >> 3;
+    const int n_groups = NBUF >= 2 ? kGroups : 1;                    // single S^T buffer: nothing to overlap
+    const int wg = (warp >> 2) & 1;
     const int lane_row = tid & 127;                  // TMEM lane owned by this thread (key in S^T, row in dQ)
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     float acc_d[2][4];                               // dTd contributions of this thread's keys
@@ -289,7 +299,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc_d[a][u] = 0.f;
     int it = 0;
-    for (int bw = bw0; bw < n_pairs; bw += stride, ++it) {
+    for (int bw = bw0; bw < n_pairs && grp < n_groups; bw += stride, ++it) {
       const int b = bw / p.P;
       const int ob = it % OPB;
       const uint8_t* opnd = smem + L.opnd0 + ob * L.opnd_bytes;
@@ -301,7 +311,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       STAMP(1);
       mbar_wait(&bar[bOpFull + ob], (it / OPB) & 1);
       STAMP(2);
-      for (int unit = 0; unit < n_units; ++unit) {
+      // (parity waits stay in step without awaiting the other group's phases: with NBUF = 3 a group has seen the S
+      //  of unit g-2, which was committed after that of g-3 = the previous phase of its buffer; with NBUF = 2 each
+      //  group owns one buffer; NBUF = 1 runs a single group.  Phases cannot run ahead of a waiter either: the next
+      //  use of a buffer needs this group's own bReady arrival.)
+      for (int unit = grp; unit < n_units; unit += n_groups) {
         const int g = it * n_units + unit, buf = g % NBUF, par = (g / NBUF) & 1;
         const int kb = unit >> 2, u = unit & 3, mt = u >> 1, hf = u & 1;
         const int nk = kb < 2 ? 128 : p.I;                         // valid keys in this block
@@ -314,68 +328,64 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         mbar_wait(&bar[bFullS + buf], par);
         tc_fence_after();
         STAMP(100);
-        uint32_t gk[16];
+        // dQ' of the query tile that used this g^T buffer before must have retired (both groups write row halves of it)
+        if (qt >= GSB) mbar_wait(&bar[bDoneQ + gs], ((qt / GSB) - 1) & 1);
         if (warp_ok) {
-          // ---- this thread: key = lane_row, rows r0 .. r0+31 ----
+          // ---- this thread: key = lane_row, rows r0 .. r0+31, in two passes of 16 (register budget: 768 threads) ----
           const int r0 = mt * 128 + hf * 64 + wg * 32;
-          uint32_t s[32], dp[32];
-          tmem_ld32(trow + cS + wg * 32, s);
-          tmem_ld32(trow + cP + wg * 32, dp);
-          tmem_wait_ld();
-          uint32_t pk[16];
+          const uint32_t cid = do_mask ? ids_s[kb * 128 + lane_row] : 0;
 #pragma unroll
-          for (int q4 = 0; q4 < 8; ++q4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(lse2_s + r0 + q4 * 4);
-            const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-            float dv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (!FOLD) {
-              const float4 d4 = *reinterpret_cast<const float4*>(delta_s + r0 + q4 * 4);
-              dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+          for (int h = 0; h < 2; ++h) {
+            uint32_t s[16], dp[16];
+            tmem_ld16(trow + cS + wg * 32 + h * 16, s);
+            tmem_ld16(trow + cP + wg * 32 + h * 16, dp);
+            tmem_wait_ld();
+            uint32_t pk[8], gk[8];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const float4 l4 = *reinterpret_cast<const float4*>(lse2_s + r0 + h * 16 + q4 * 4);
+              const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+              float dv[4] = {0.f, 0.f, 0.f, 0.f};
+              if (!FOLD) {
+                const float4 d4 = *reinterpret_cast<const float4*>(delta_s + r0 + h * 16 + q4 * 4);
+                dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+              }
+              float pv[4], gv[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int r = q4 * 4 + e;
+                pv[e] = fast_exp2(fmaf(__uint_as_float(s[r]), c2, -lv[e]));
+                gv[e] = pv[e] * (FOLD ? __uint_as_float(dp[r]) : __uint_as_float(dp[r]) - dv[e]);
+              }
+              pk[q4 * 2] = pack_bf16(pv[0], pv[1]);
+              pk[q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
+              gk[q4 * 2] = pack_bf16(gv[0], gv[1]);
+              gk[q4 * 2 + 1] = pack_bf16(gv[2], gv[3]);
             }
-            float pv[4], gv[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int r = q4 * 4 + e;
-              pv[e] = fast_exp2(fmaf(__uint_as_float(s[r]), c2, -lv[e]));
-              gv[e] = pv[e] * (FOLD ? __uint_as_float(dp[r]) : __uint_as_float(dp[r]) - dv[e]);
-            }
-            pk[q4 * 2] = pack_bf16(pv[0], pv[1]);
-            pk[q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
-            gk[q4 * 2] = pack_bf16(gv[0], gv[1]);
-            gk[q4 * 2 + 1] = pack_bf16(gv[2], gv[3]);
-          }
-          if (do_mask) {
-            const uint32_t cid = ids_s[kb * 128 + lane_row];
-            const uint4* sp = reinterpret_cast<const uint4*>(sel_s + id_slot(cid) * (kN / 4) + r0 / 4);
-            const uint4* wpp = reinterpret_cast<const uint4*>(wp_s + r0);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              const uint4 s4 = sp[h];
+            if (do_mask) {
+              const uint4 s4 = *reinterpret_cast<const uint4*>(sel_s + id_slot(cid) * (kN / 4) + r0 / 4 + h * 4);
               const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
-              const uint4 wa = wpp[h * 2], wb = wpp[h * 2 + 1];
+              const uint4* wpp = reinterpret_cast<const uint4*>(wp_s + r0 + h * 16);
+              const uint4 wa = wpp[0], wb = wpp[1];
               const uint32_t ww[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
 #pragma unroll
               for (int w = 0; w < 4; ++w) {
-                pk[h * 8 + w * 2] = prmt(pk[h * 8 + w * 2], ww[w * 2], sw[w]);
-                pk[h * 8 + w * 2 + 1] = prmt(pk[h * 8 + w * 2 + 1], ww[w * 2 + 1], sw[w] >> 16);
-                gk[h * 8 + w * 2] = prmt(gk[h * 8 + w * 2], 0u, sw[w]);
-                gk[h * 8 + w * 2 + 1] = prmt(gk[h * 8 + w * 2 + 1], 0u, sw[w] >> 16);
+                pk[w * 2] = prmt(pk[w * 2], ww[w * 2], sw[w]);
+                pk[w * 2 + 1] = prmt(pk[w * 2 + 1], ww[w * 2 + 1], sw[w] >> 16);
+                gk[w * 2] = prmt(gk[w * 2], 0u, sw[w]);
+                gk[w * 2 + 1] = prmt(gk[w * 2 + 1], 0u, sw[w] >> 16);
               }
+            }
+            tmem_st8(trow + cS + wg * 32 + h * 8, pk);             // packed over this warpgroup's own consumed columns
+            tmem_st8(trow + cP + wg * 32 + h * 8, gk);
+            // g^T -> smem as the MN-major A operand of dQ = g.K : [row group of 8][key group of 8][key%8][16 B]
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const int rg = (hf * 64 + wg * 32) / 8 + h * 2 + q;
+              *reinterpret_cast<uint4*>(Gs + rg * 2048 + lane_row * 16) = make_uint4(gk[q * 4], gk[q * 4 + 1], gk[q * 4 + 2], gk[q * 4 + 3]);
             }
           }
           STAMP(102);
-          tmem_st16(trow + cS + wg * 32, pk);                      // packed over this warpgroup's own consumed columns
-          tmem_st16(trow + cP + wg * 32, gk);
-        }
-        // dQ' of the query tile that used this g^T buffer before must have retired
-        if (hf == 0 && qt >= GSB) mbar_wait(&bar[bDoneQ + gs], ((qt / GSB) - 1) & 1);
-        if (warp_ok) {
-          // g^T -> smem as the MN-major A operand of dQ = g.K : [row group of 8][key group of 8][key%8][16 B]
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int rg = (hf * 64 + wg * 32) / 8 + q;
-            *reinterpret_cast<uint4*>(Gs + rg * 2048 + lane_row * 16) = make_uint4(gk[q * 4], gk[q * 4 + 1], gk[q * 4 + 2], gk[q * 4 + 3]);
-          }
           tmem_wait_st();
         }
         fence_proxy_async_smem();
@@ -437,8 +447,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
           STAMP(109);
         }
       }
-      // ---- all key blocks done: dQ' tiles (warpgroup w drains query tile w) ----
-      {
+      // ---- all key blocks done: dQ' tiles (group 1 finishes the last unit: its warpgroup w drains query tile w) ----
+      if (grp == n_groups - 1) {
         const int qt_last = it * n_kb * 2 + n_kb * 2 - 1;
         for (int q = qt_last - GSB + 1; q <= qt_last; ++q) mbar_wait(&bar[bDoneQ + q % GSB], (q / GSB) & 1);   // not yet awaited
         tc_fence_after();
@@ -463,7 +473,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     // dKaug[key][u] = sum over all rows/windows of g * onehot: columns [0,wh) -> dTh[u][jh(key)], [wh,wh+ww) -> dTw[u][jw(key)];
     // for prompt keys the wh replicated columns sum to dtok[i].  The /scale of K'aug and the *scale of dS cancel.
     // (the last dKaug chain retired with the last key block: bDoneC counts all three chains)
-    if (it > 0) {
+    if (it > 0 && grp == n_groups - 1) {
       for (int kb = wg; kb < n_kb; kb += 2) {
         uint32_t o[16];
         tmem_ld16(trow + cAUG + kb * 16, o);
@@ -494,12 +504,13 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         }
       }
       comp_sync();
-      for (int i = tid; i < p.wh * p.wh; i += kCompute) atomicAdd(&p.dth[head * p.wh * p.wh + i], gth_s[i]);
-      for (int i = tid; i < p.ww * p.ww; i += kCompute) atomicAdd(&p.dtw[head * p.ww * p.ww + i], gtw_s[i]);
-      for (int i = tid; i < p.wd * p.wd; i += kCompute) atomicAdd(&p.dtd[head * p.wd * p.wd + i], gtd_s[i]);
-      for (int i = tid; i < p.I; i += kCompute) atomicAdd(&p.dtok[head * p.I + i], gtok_s[i]);
+      const int ct = tid - (n_groups - 1) * kCompute;
+      for (int i = ct; i < p.wh * p.wh; i += kCompute) atomicAdd(&p.dth[head * p.wh * p.wh + i], gth_s[i]);
+      for (int i = ct; i < p.ww * p.ww; i += kCompute) atomicAdd(&p.dtw[head * p.ww * p.ww + i], gtw_s[i]);
+      for (int i = ct; i < p.wd * p.wd; i += kCompute) atomicAdd(&p.dtd[head * p.wd * p.wd + i], gtd_s[i]);
+      for (int i = ct; i < p.I; i += kCompute) atomicAdd(&p.dtok[head * p.I + i], gtok_s[i]);
     }
-  } else if (warp < 13) {
+  } else if (warp < kProd0) {
     // =============================================================================================
     // MMA issuers (one lane each)
     // =============================================================================================
@@ -509,7 +520,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       const uint32_t idescDK = make_idesc_bf16(128, DKC, 0, 1);     // dK' : A tmem, B = Q' MN-major
       const uint32_t idescAUG = make_idesc_bf16(128, 16, 0, 1);     // dKaug
       const uint32_t idescDQ = make_idesc_bf16(128, DKC, 1, 1);     // dQ' : A = g smem MN-major, B = K' MN-major
-      const int role = warp - 8;                                    // 0 S, 1 V, 2 K, 3 A, 4 Q
+      const int role = warp - kIssue0;                              // 0 S, 1 V, 2 K, 3 A, 4 Q
       int it = 0;
       for (int bw = bw0; bw < n_pairs; bw += stride, ++it) {
         const int ob = it % OPB;
@@ -576,6 +587,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
           } else {
             // (every unit's barrier phase is awaited in order, so that a parity wait can never lag two phases behind)
             mbar_wait(&bar[bReady + buf], par);
+            STAMP(10 + unit);
             if (hf == 0) continue;
             // dQ'[mt] += g[128 rows x nk keys] . K'[kb]
             const int nk = kb < 2 ? 128 : p.I;
@@ -589,6 +601,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
               mma_ss(tmem + cDQ + mt * DKC, da, db, idescDQ, (kb > 0) | (t > 0));
             }
             mma_commit(&bar[bDoneQ + gs]);
+            STAMP(100);
           }
         }
       }
@@ -597,7 +610,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     // =============================================================================================
     // staging warps: global -> smem operand buffer of window `it` (one window ahead of the consumers when OPB = 2)
     // =============================================================================================
-    const int pt = tid - 13 * 32;
+    const int pt = tid - kProd0 * 32;
     int it = 0;
     for (int bw = bw0; bw < n_pairs; bw += stride, ++it) {
       const int b = bw / p.P, win = bw - b * p.P;

@@ -1,4 +1,5 @@
-"""Debug: per-unit clock64 timeline of CTA 0 of the backward attention kernel (PWA_TIMELINE=1)."""
+"""Debug: merged clock64 timeline of CTA 0 of the backward attention kernel (PWA_TIMELINE=1): compute group 0 / 1
+(thread 0 of each), S / V / Q issuers and the staging warp, for one steady-state window."""
 import os, sys
 os.environ["PWA_TIMELINE"] = "1"
 import torch
@@ -8,7 +9,7 @@ import pwa_b200
 from pwa_b200 import functional as PF
 dev = torch.device("cuda")
 B, C, heads, I, WS = 4, 48, 4, 64, (8, 8, 4)
-shifted = len(sys.argv) > 1
+shifted = len(sys.argv) > 1 and sys.argv[1] == "s"
 g = pwa_b200.get_geometry((48, 48, 48), WS, (4, 4, 2) if shifted else (0, 0, 0))
 qkv = torch.randn(B, g.P, g.N, 3 * C, device=dev).to(torch.bfloat16).requires_grad_(True)
 kvp = torch.randn(B, I, 2 * C, device=dev).to(torch.bfloat16).requires_grad_(True)
@@ -20,14 +21,17 @@ for _ in range(2):
     out.backward(torch.randn_like(out))
 torch.cuda.synchronize()
 d = PF._WindowAttentionPacked.last_delta.reshape(-1).view(torch.int64).cpu()
-for name, base in (("compute tid0", 0), ("S issuer", 2048), ("V issuer", 4096), ("producer", 6144)):
+names = {0: "cA", 8192: "cB", 2048: "S", 4096: "V", 10240: "Q", 6144: "P"}
+allev = []
+for base, nm in names.items():
     ev = [(int(d[base + 2 * i]), int(d[base + 2 * i + 1])) for i in range(1000)]
-    ev = [e for e in ev if 0 < e[1] < 200]
-    # second window of this CTA: from the 2nd tag==1 to the 3rd
-    starts = [i for i, e in enumerate(ev) if e[1] == 1]
-    if len(starts) < 3:
-        print(name, "not enough events", len(ev)); continue
-    seg = ev[starts[1]:starts[2] + 1]
-    t0 = seg[0][0]
-    print(name, "window total clk", seg[-1][0] - t0)
-    print(" ".join(f"{tag}:{t - t0}" for t, tag in seg))
+    allev += [(t, nm, tag) for t, tag in ev if 0 < tag < 200 and t > 0]
+ca = [(t, tag) for t, nm, tag in allev if nm == "cA"]
+starts = [t for t, tag in ca if tag == 1]
+if len(starts) < 4:
+    print("not enough events", len(ca)); sys.exit(0)
+t0, t1 = starts[2], starts[3]
+print("window clk", t1 - t0)
+for t, nm, tag in sorted(allev):
+    if t0 - 200 <= t <= t1 + 200:
+        print(f"{t - t0:7d} {nm:>3} {tag}")

@@ -175,6 +175,14 @@ int pwa_ln_fwd(const void* x, const void* res, const float* gamma, const float* 
 int pwa_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int dtype, void* stream);
 
+/* pwa_ln_bwd plus two optional fp32 [C] column sums over all rows (NULL = skip; zeroed by this call):
+ * dres_colsum = sum_rows dres and dx_colsum = sum_rows dx.  In the block, dx is the gradient of `proj(o) + bias`
+ * (window_attention.py:59) and dres that of `mlp(...) + bias` (swin_block.py:227), so these ARE the two Linear bias
+ * gradients and come out of a pass that reads the tensors anyway. */
+int pwa_ln_bwd2(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                const void* dres, void* dx, float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
+                int64_t rows, int C, int dtype, void* stream);
+
 /* 1 iff the bf16 tcgen05 kernel supports this shape (else impl=0 falls back to the fp32-math kernel). */
 int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype);
 

@@ -60,7 +60,8 @@ def _load():
     i64, f32 = C.c_int64, C.c_float
     lib.pwa_ln_fwd.argtypes = [vp, vp, f32p, f32p, vp, vp, f32p, f32p, i64, i32, f32, i32, vp]
     lib.pwa_ln_bwd.argtypes = [vp, vp, f32p, f32p, f32p, vp, vp, f32p, f32p, i64, i32, i32, vp]
-    lib.pwa_ln_fwd.restype = lib.pwa_ln_bwd.restype = i32
+    lib.pwa_ln_bwd2.argtypes = [vp, vp, f32p, f32p, f32p, vp, vp, f32p, f32p, f32p, f32p, i64, i32, i32, vp]
+    lib.pwa_ln_fwd.restype = lib.pwa_ln_bwd.restype = lib.pwa_ln_bwd2.restype = i32
     i32p = C.POINTER(i32)
     lib.pwa_bias_tables_fwd.argtypes = [f32p] * 8 + [f32p] * 4 + [i32, i32, i32p, i32p, i32, vp]
     lib.pwa_bias_tables_bwd.argtypes = [f32p] * 8 + [f32p] * 4 + [f32p] * 8 + [i32, i32, i32p, i32p, i32, vp]
@@ -75,7 +76,7 @@ lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
                     "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
-                    "pwa_ln_fwd", "pwa_ln_bwd", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
+                    "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 
 def check(rc: int, what: str):

@@ -6,38 +6,62 @@
 //   forward : s = x (+ res) ; y = (s - mean) * rstd * gamma + beta ; saves mean, rstd   (also writes s if res)
 //   backward: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres), g = dy * gamma ;
 //             dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy   (register partials -> smem -> fp32 atomics)
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pwa {
 
 constexpr int kLnThreads = 256;
-constexpr int kLnMaxNV = 8;   // vectors of 4 per lane -> C <= 32 * 8 * 4 = 1024
 
-template <typename T> struct Vec4;
-template <> struct Vec4<float> {
+// 16-byte lane vectors where the row length allows (8 bf16 / 4 fp32), else 8-byte (4 bf16)
+template <typename T, int EPV> struct Vec;
+template <> struct Vec<float, 4> {
   static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
-    const float4 t = *reinterpret_cast<const float4*>(p);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
   }
   static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
     *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   }
 };
-template <> struct Vec4<__nv_bfloat16> {
+__device__ __forceinline__ void unpack2(uint32_t w, float& a, float& b) {
+  a = __uint_as_float(w << 16);
+  b = __uint_as_float(w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+template <> struct Vec<__nv_bfloat16, 4> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[4]) {
-    const uint2 t = *reinterpret_cast<const uint2*>(p);
-    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
-    const __nv_bfloat162 b = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
-    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(b); v[3] = __high2float(b);
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    unpack2(t.x, v[0], v[1]);
+    unpack2(t.y, v[2], v[3]);
   }
   static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[4]) {
-    __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 t;
-    t.x = *reinterpret_cast<uint32_t*>(&a);
-    t.y = *reinterpret_cast<uint32_t*>(&b);
-    *reinterpret_cast<uint2*>(p) = t;
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
   }
 };
+template <> struct Vec<__nv_bfloat16, 8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&v)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p));
+    unpack2(t.x, v[0], v[1]);
+    unpack2(t.y, v[2], v[3]);
+    unpack2(t.z, v[4], v[5]);
+    unpack2(t.w, v[6], v[7]);
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float (&v)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+  }
+};
+template <int EPV> __device__ __forceinline__ void loadf(const float* p, float (&v)[EPV]) {
+#pragma unroll
+  for (int e = 0; e < EPV; e += 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p + e));
+    v[e] = t.x; v[e + 1] = t.y; v[e + 2] = t.z; v[e + 3] = t.w;
+  }
+}
 
 template <int G>
 __device__ __forceinline__ float group_sum(float v) {
@@ -46,159 +70,207 @@ __device__ __forceinline__ float group_sum(float v) {
   return v;
 }
 
-template <typename T, int G, int NV>
-__global__ void __launch_bounds__(kLnThreads) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
+// A row is handled by a group of G lanes, each lane owning NV vectors of EPV elements; every group works on R rows
+// per iteration with all of their loads issued before the first use (memory-level parallelism: these kernels are
+// pure HBM streams of 2-4 passes over [rows, C]).
+template <typename T, int G, int NV, int EPV, int R>
+__global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 16 ? 4 : (NV * EPV * R <= 32 ? 2 : 1))) ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
                                                             T* __restrict__ sum_out, T* __restrict__ y,
                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                             long rows, int C, float eps) {
-  constexpr int RPB = kLnThreads / G;                  // rows per block-iteration
+  constexpr int GPB = kLnThreads / G;                  // groups per block
   const int gl = threadIdx.x % G, gr = threadIdx.x / G;
-  const int nvec = C / 4;
-  float gm[NV][4], bt[NV][4];
+  const int nvec = C / EPV;
+  float gm[NV][EPV], bt[NV][EPV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int vi = gl + k * G;
     if (vi < nvec) {
-      Vec4<float>::load(gamma + vi * 4, gm[k]);
-      Vec4<float>::load(beta + vi * 4, bt[k]);
+      loadf<EPV>(gamma + vi * EPV, gm[k]);
+      loadf<EPV>(beta + vi * EPV, bt[k]);
     }
   }
   const float invC = 1.f / (float)C;
+  const bool has_res = res != nullptr;
   // the loop bound is uniform per CTA so that the sub-warp shuffles always run with all 32 lanes
-  for (long base = (long)blockIdx.x * RPB; base < rows; base += (long)gridDim.x * RPB) {
-    const long row = base + gr;
-    const bool live = row < rows;
-    float v[NV][4];
-    float s = 0.f;
+  for (long base = (long)blockIdx.x * (GPB * R); base < rows; base += (long)gridDim.x * (GPB * R)) {
+    float v[R][NV][EPV], rr[R][NV][EPV];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int vi = gl + k * G;
+    for (int r = 0; r < R; ++r) {
+      const long row = base + r * GPB + gr;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) v[k][e] = 0.f;
-      if (vi < nvec && live) {
-        Vec4<T>::load(x + row * C + vi * 4, v[k]);
-        if (res != nullptr) {
-          float r[4];
-          Vec4<T>::load(res + row * C + vi * 4, r);
+      for (int k = 0; k < NV; ++k) {
+        const int vi = gl + k * G;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) v[k][e] += r[e];
-          // the residual sum is stored in the I/O dtype and the statistics use the STORED value
-          Vec4<T>::store(sum_out + row * C + vi * 4, v[k]);
-          if (sizeof(T) == 2) {
+        for (int e = 0; e < EPV; ++e) v[r][k][e] = rr[r][k][e] = 0.f;
+        if (vi < nvec && row < rows) {
+          Vec<T, EPV>::load(x + row * C + vi * EPV, v[r][k]);
+          if (has_res) Vec<T, EPV>::load(res + row * C + vi * EPV, rr[r][k]);
+        }
+      }
+    }
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[k][e] = to_f32(from_f32<T>(v[k][e]));
+    for (int r = 0; r < R; ++r) {
+      const long row = base + r * GPB + gr;
+      const bool live = row < rows;
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int vi = gl + k * G;
+        if (vi < nvec && live) {
+          if (has_res) {
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) v[r][k][e] += rr[r][k][e];
+            // the residual sum is stored in the I/O dtype and the statistics use the STORED value
+            Vec<T, EPV>::store(sum_out + row * C + vi * EPV, v[r][k]);
+            if (sizeof(T) == 2) {
+#pragma unroll
+              for (int e = 0; e < EPV; ++e) v[r][k][e] = to_f32(from_f32<T>(v[r][k][e]));
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) s += v[r][k][e];
+        }
+      }
+      const float mean = group_sum<G>(s) * invC;
+      float q = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int vi = gl + k * G;
+        if (vi < nvec) {
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) {
+            const float d = v[r][k][e] - mean;
+            q = fmaf(d, d, q);
           }
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) s += v[k][e];
       }
-    }
-    const float mean = group_sum<G>(s) * invC;
-    float q = 0.f;
+      const float rstd = rsqrtf(group_sum<G>(q) * invC + eps);
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int vi = gl + k * G;
-      if (vi < nvec) {
+      for (int k = 0; k < NV; ++k) {
+        const int vi = gl + k * G;
+        if (vi < nvec && live) {
+          float o[EPV];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float d = v[k][e] - mean;
-          q = fmaf(d, d, q);
+          for (int e = 0; e < EPV; ++e) o[e] = fmaf((v[r][k][e] - mean) * rstd, gm[k][e], bt[k][e]);
+          Vec<T, EPV>::store(y + row * C + vi * EPV, o);
         }
       }
-    }
-    const float rstd = rsqrtf(group_sum<G>(q) * invC + eps);
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int vi = gl + k * G;
-      if (vi < nvec && live) {
-        float o[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = fmaf((v[k][e] - mean) * rstd, gm[k][e], bt[k][e]);
-        Vec4<T>::store(y + row * C + vi * 4, o);
+      if (gl == 0 && live) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
       }
-    }
-    if (gl == 0 && live) {
-      mean_out[row] = mean;
-      rstd_out[row] = rstd;
     }
   }
 }
 
-template <typename T, int G, int NV>
-__global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
+// dres_colsum / dx_colsum (optional, fp32 [C]): column sums over all rows of the residual-path gradient and of the
+// produced dx -- the gradients of the Linear biases on either side of this LayerNorm (swin_block.py:222,227: dx is
+// the gradient of `proj(...) + bias`, dres that of `mlp(...) + bias`), which saves two full reduction passes.
+template <typename T, int G, int NV, int EPV, int R>
+__global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 8 ? 4 : (NV * EPV * R <= 16 ? 2 : 1))) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, const T* __restrict__ dres,
                                                             T* __restrict__ dx, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, long rows, int C) {
-  constexpr int RPB = kLnThreads / G;
-  extern __shared__ float red[];                        // [2][C]
+                                                            float* __restrict__ dbeta, float* __restrict__ dres_colsum,
+                                                            float* __restrict__ dx_colsum, long rows, int C) {
+  constexpr int GPB = kLnThreads / G;
+  extern __shared__ float red[];                        // [4][C]
   const int gl = threadIdx.x % G, gr = threadIdx.x / G;
-  const int nvec = C / 4;
-  for (int i = threadIdx.x; i < 2 * C; i += kLnThreads) red[i] = 0.f;
-  float gm[NV][4], ag[NV][4], ab[NV][4];
+  const int nvec = C / EPV;
+  const bool has_res = dres != nullptr;
+  const bool want_rs = dres_colsum != nullptr && has_res, want_xs = dx_colsum != nullptr;
+  for (int i = threadIdx.x; i < 4 * C; i += kLnThreads) red[i] = 0.f;
+  float gm[NV][EPV], ag[NV][EPV], ab[NV][EPV], ar[NV][EPV], ax[NV][EPV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int vi = gl + k * G;
-    if (vi < nvec) Vec4<float>::load(gamma + vi * 4, gm[k]);
+    if (vi < nvec) loadf<EPV>(gamma + vi * EPV, gm[k]);
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ag[k][e] = ab[k][e] = 0.f;
+    for (int e = 0; e < EPV; ++e) ag[k][e] = ab[k][e] = ar[k][e] = ax[k][e] = 0.f;
   }
   const float invC = 1.f / (float)C;
-  for (long base = (long)blockIdx.x * RPB; base < rows; base += (long)gridDim.x * RPB) {
-    const long row = base + gr;
-    const bool live = row < rows;
-    const float mean = live ? mean_in[row] : 0.f, rstd = live ? rstd_in[row] : 0.f;
-    float g[NV][4], xh[NV][4];
-    float s1 = 0.f, s2 = 0.f;
+  for (long base = (long)blockIdx.x * (GPB * R); base < rows; base += (long)gridDim.x * (GPB * R)) {
+    float d[R][NV][EPV], xv[R][NV][EPV], rs[R][NV][EPV];
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int vi = gl + k * G;
+    for (int r = 0; r < R; ++r) {
+      const long row = base + r * GPB + gr;
+      const bool live = row < rows;
+      mean[r] = live ? __ldg(mean_in + row) : 0.f;
+      rstd[r] = live ? __ldg(rstd_in + row) : 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) g[k][e] = xh[k][e] = 0.f;
-      if (vi < nvec && live) {
-        float d[4], xv[4];
-        Vec4<T>::load(dy + row * C + vi * 4, d);
-        Vec4<T>::load(x + row * C + vi * 4, xv);
+      for (int k = 0; k < NV; ++k) {
+        const int vi = gl + k * G;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          xh[k][e] = (xv[e] - mean) * rstd;
-          g[k][e] = d[e] * gm[k][e];
-          s1 += g[k][e];
-          s2 = fmaf(g[k][e], xh[k][e], s2);
-          ag[k][e] = fmaf(d[e], xh[k][e], ag[k][e]);
-          ab[k][e] += d[e];
+        for (int e = 0; e < EPV; ++e) d[r][k][e] = xv[r][k][e] = rs[r][k][e] = 0.f;
+        if (vi < nvec && live) {
+          Vec<T, EPV>::load(dy + row * C + vi * EPV, d[r][k]);
+          Vec<T, EPV>::load(x + row * C + vi * EPV, xv[r][k]);
+          if (has_res) Vec<T, EPV>::load(dres + row * C + vi * EPV, rs[r][k]);
         }
       }
     }
-    s1 = group_sum<G>(s1) * invC;
-    s2 = group_sum<G>(s2) * invC;
 #pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int vi = gl + k * G;
-      if (vi < nvec && live) {
-        float o[4];
+    for (int r = 0; r < R; ++r) {
+      const long row = base + r * GPB + gr;
+      const bool live = row < rows;
+      float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = rstd * (g[k][e] - s1 - xh[k][e] * s2);
-        if (dres != nullptr) {
-          float r[4];
-          Vec4<T>::load(dres + row * C + vi * 4, r);
+      for (int k = 0; k < NV; ++k) {
+        if (gl + k * G >= nvec) continue;                 // (dead rows hold zeros and mean = rstd = 0: they add nothing)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] += r[e];
+        for (int e = 0; e < EPV; ++e) {
+          const float xh = (xv[r][k][e] - mean[r]) * rstd[r];
+          const float g = d[r][k][e] * gm[k][e];
+          xv[r][k][e] = xh;
+          s1 += g;
+          s2 = fmaf(g, xh, s2);
+          ag[k][e] = fmaf(d[r][k][e], xh, ag[k][e]);
+          ab[k][e] += d[r][k][e];
+          d[r][k][e] = g;
         }
-        Vec4<T>::store(dx + row * C + vi * 4, o);
+      }
+      s1 = group_sum<G>(s1) * invC;
+      s2 = group_sum<G>(s2) * invC;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int vi = gl + k * G;
+        if (vi < nvec && live) {
+          float o[EPV];
+#pragma unroll
+          for (int e = 0; e < EPV; ++e) {
+            o[e] = rstd[r] * (d[r][k][e] - s1 - xv[r][k][e] * s2) + rs[r][k][e];
+            ar[k][e] += rs[r][k][e];
+            ax[k][e] += o[e];
+          }
+          Vec<T, EPV>::store(dx + row * C + vi * EPV, o);
+        }
       }
     }
   }
   __syncthreads();
+  // column sums: first across the 32/G row groups of a warp (lanes with equal gl) by shuffles, then one
+  // shared-memory atomic per warp and column (8-way instead of 256/G-way contention), then one global atomic per CTA
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int vi = gl + k * G;
-    if (vi < nvec) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        atomicAdd(&red[vi * 4 + e], ag[k][e]);
-        atomicAdd(&red[C + vi * 4 + e], ab[k][e]);
+    for (int e = 0; e < EPV; ++e) {
+      float a = ag[k][e], b = ab[k][e], c = ar[k][e], d = ax[k][e];
+#pragma unroll
+      for (int o = G; o < 32; o <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (want_rs) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (want_xs) d += __shfl_xor_sync(0xffffffffu, d, o);
+      }
+      if ((threadIdx.x & 31) < G && vi < nvec) {
+        atomicAdd(&red[vi * EPV + e], a);
+        atomicAdd(&red[C + vi * EPV + e], b);
+        if (want_rs) atomicAdd(&red[2 * C + vi * EPV + e], c);
+        if (want_xs) atomicAdd(&red[3 * C + vi * EPV + e], d);
       }
     }
   }
@@ -206,43 +278,76 @@ __global__ void __launch_bounds__(kLnThreads) ln_bwd_kernel(const T* __restrict_
   for (int i = threadIdx.x; i < C; i += kLnThreads) {
     atomicAdd(&dgamma[i], red[i]);
     atomicAdd(&dbeta[i], red[C + i]);
+    if (want_rs) atomicAdd(&dres_colsum[i], red[2 * C + i]);
+    if (want_xs) atomicAdd(&dx_colsum[i], red[3 * C + i]);
   }
 }
 
-template <typename T, int G, int NV>
-static int ln_launch(bool fwd, const void* a, const void* b, const float* gamma, const float* beta_or_mean, const float* rstd,
-                     const void* res, void* o1, void* o2, float* f1, float* f2, long rows, int C, float eps, cudaStream_t st) {
-  constexpr int RPB = kLnThreads / G;
-  long blocks = (rows + RPB - 1) / RPB;
-  const long cap = fwd ? 148L * 16 : 148L * 4;        // backward: fewer CTAs -> fewer global atomics
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+struct LnArgs {
+  const void *a, *b, *res;
+  const float *gamma, *bm, *rstd;
+  void *o1, *o2;
+  float *f1, *f2, *f3, *f4;
+  long rows;
+  int C;
+  float eps;
+};
+
+template <typename T, int G, int NV, int EPV, int R>
+static int ln_launch(bool fwd, const LnArgs& a, cudaStream_t st) {
+  constexpr int GPB = kLnThreads / G;
+  long blocks = (a.rows + GPB * R - 1) / (GPB * R);
+  // backward: fewer CTAs -> fewer global atomics
+  const long cap = 148L * (fwd ? env_int("PWA_LN_CAPF", 8) : env_int("PWA_LN_CAPB", 4));
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (fwd) {
-    ln_fwd_kernel<T, G, NV><<<(unsigned)blocks, kLnThreads, 0, st>>>((const T*)a, (const T*)res, gamma, beta_or_mean, (T*)o1,
-                                                                      (T*)o2, f1, f2, rows, C, eps);
+    ln_fwd_kernel<T, G, NV, EPV, R><<<(unsigned)blocks, kLnThreads, 0, st>>>((const T*)a.a, (const T*)a.res, a.gamma, a.bm,
+                                                                              (T*)a.o1, (T*)a.o2, a.f1, a.f2, a.rows, a.C, a.eps);
   } else {
-    ln_bwd_kernel<T, G, NV><<<(unsigned)blocks, kLnThreads, 2 * C * sizeof(float), st>>>(
-        (const T*)a, (const T*)b, gamma, beta_or_mean, rstd, (const T*)res, (T*)o1, f1, f2, rows, C);
+    ln_bwd_kernel<T, G, NV, EPV, R><<<(unsigned)blocks, kLnThreads, 4 * a.C * sizeof(float), st>>>(
+        (const T*)a.a, (const T*)a.b, a.gamma, a.bm, a.rstd, (const T*)a.res, (T*)a.o1, a.f1, a.f2, a.f3, a.f4, a.rows, a.C);
   }
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }
 
-template <typename T>
-static int ln_dispatch(bool fwd, const void* a, const void* b, const float* gamma, const float* bm, const float* rstd,
-                       const void* res, void* o1, void* o2, float* f1, float* f2, long rows, int C, float eps, cudaStream_t st) {
-  const int nvec = C / 4;
-#define LN_CASE(G, NV) return ln_launch<T, G, NV>(fwd, a, b, gamma, bm, rstd, res, o1, o2, f1, f2, rows, C, eps, st)
-  if (nvec <= 4) LN_CASE(4, 1);
-  if (nvec <= 8) LN_CASE(8, 1);
-  if (nvec <= 16) LN_CASE(16, 1);
-  if (nvec <= 32) LN_CASE(32, 1);
-  if (nvec <= 64) LN_CASE(32, 2);
-  if (nvec <= 128) LN_CASE(32, 4);
-  if (nvec <= 256) LN_CASE(32, 8);
+template <typename T, int EPV>
+static int ln_dispatch_v(bool fwd, const LnArgs& a, cudaStream_t st) {
+  const int nvec = a.C / EPV;
+  const int R = env_int(fwd ? "PWA_LN_RF" : "PWA_LN_RB", 1);       // rows per group per iteration (tuning knob)
+#define LN_CASE(G, NV, R) return ln_launch<T, G, NV, EPV, R>(fwd, a, st)
+#define LN_CASE_R(G)                    \
+  do {                                  \
+    if (R >= 4) LN_CASE(G, 1, 4);       \
+    if (R == 2) LN_CASE(G, 1, 2);       \
+    LN_CASE(G, 1, 1);                   \
+  } while (0)
+  if (nvec <= 4) LN_CASE_R(4);
+  if (nvec <= 8) LN_CASE_R(8);
+  if (nvec <= 16) LN_CASE_R(16);
+  if (nvec <= 32) LN_CASE_R(32);
+  if (nvec <= 64) LN_CASE(32, 2, 1);
+  if (nvec <= 128) LN_CASE(32, 4, 1);
+  if (EPV == 4 && nvec <= 256) LN_CASE(32, 8, 1);
+#undef LN_CASE_R
 #undef LN_CASE
-  set_error("layer norm: C=%d too large (max 1024)", C);
+  set_error("layer norm: C=%d too large (max 1024)", a.C);
   return PWA_ERR_UNSUPPORTED;
+}
+
+template <typename T>
+static int ln_dispatch(bool fwd, const LnArgs& a, cudaStream_t st) {
+  if constexpr (sizeof(T) == 2) {
+    const uintptr_t al = (uintptr_t)a.a | (uintptr_t)a.b | (uintptr_t)a.res | (uintptr_t)a.o1 | (uintptr_t)a.o2;
+    if (a.C % 8 == 0 && (al & 15) == 0 && env_int("PWA_LN_EPV", 8) == 8) return ln_dispatch_v<T, 8>(fwd, a, st);
+  }
+  return ln_dispatch_v<T, 4>(fwd, a, st);
 }
 
 }  // namespace pwa
@@ -253,24 +358,33 @@ extern "C" int pwa_ln_fwd(const void* x, const void* res, const float* gamma, co
                           float* mean, float* rstd, int64_t rows, int C, float eps, int dtype, void* stream) {
   PWA_CHECK_ARG(x && gamma && beta && y && mean && rstd, "pwa_ln_fwd: null pointer");
   PWA_CHECK_ARG(res == nullptr || sum_out != nullptr, "pwa_ln_fwd: residual given without sum_out");
-  PWA_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0, "pwa_ln_fwd: need C %% 4 == 0 (C=%d)", C);
+  PWA_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0 && C <= 1024, "pwa_ln_fwd: need C %% 4 == 0, C <= 1024 (C=%d)", C);
   PWA_CHECK_ARG(dtype == PWA_F32 || dtype == PWA_BF16, "pwa_ln_fwd: bad dtype %d", dtype);
   if (rows == 0) return PWA_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == PWA_F32 ? ln_dispatch<float>(true, x, nullptr, gamma, beta, nullptr, res, sum_out, y, mean, rstd, rows, C, eps, st)
-                          : ln_dispatch<__nv_bfloat16>(true, x, nullptr, gamma, beta, nullptr, res, sum_out, y, mean, rstd, rows, C, eps, st);
+  LnArgs a = {x, nullptr, res, gamma, beta, nullptr, sum_out, y, mean, rstd, nullptr, nullptr, (long)rows, C, eps};
+  return dtype == PWA_F32 ? ln_dispatch<float>(true, a, st) : ln_dispatch<__nv_bfloat16>(true, a, st);
+}
+
+extern "C" int pwa_ln_bwd2(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
+                           const void* dres, void* dx, float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
+                           int64_t rows, int C, int dtype, void* stream) {
+  PWA_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "pwa_ln_bwd: null pointer");
+  PWA_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0 && C <= 1024, "pwa_ln_bwd: need C %% 4 == 0, C <= 1024 (C=%d)", C);
+  PWA_CHECK_ARG(dtype == PWA_F32 || dtype == PWA_BF16, "pwa_ln_bwd: bad dtype %d", dtype);
+  PWA_CHECK_ARG(dres_colsum == nullptr || dres != nullptr, "pwa_ln_bwd: dres_colsum without dres");
+  cudaStream_t st = (cudaStream_t)stream;
+  PWA_CUDA_OK(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
+  PWA_CUDA_OK(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
+  if (dres_colsum) PWA_CUDA_OK(cudaMemsetAsync(dres_colsum, 0, (size_t)C * 4, st));
+  if (dx_colsum) PWA_CUDA_OK(cudaMemsetAsync(dx_colsum, 0, (size_t)C * 4, st));
+  if (rows == 0) return PWA_OK;
+  LnArgs a = {dy, x, dres, gamma, mean, rstd, dx, nullptr, dgamma, dbeta, dres_colsum, dx_colsum, (long)rows, C, 0.f};
+  return dtype == PWA_F32 ? ln_dispatch<float>(false, a, st) : ln_dispatch<__nv_bfloat16>(false, a, st);
 }
 
 extern "C" int pwa_ln_bwd(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                           const void* dres, void* dx, float* dgamma, float* dbeta, int64_t rows, int C, int dtype,
                           void* stream) {
-  PWA_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta, "pwa_ln_bwd: null pointer");
-  PWA_CHECK_ARG(rows >= 0 && C > 0 && C % 4 == 0, "pwa_ln_bwd: need C %% 4 == 0 (C=%d)", C);
-  PWA_CHECK_ARG(dtype == PWA_F32 || dtype == PWA_BF16, "pwa_ln_bwd: bad dtype %d", dtype);
-  cudaStream_t st = (cudaStream_t)stream;
-  PWA_CUDA_OK(cudaMemsetAsync(dgamma, 0, (size_t)C * 4, st));
-  PWA_CUDA_OK(cudaMemsetAsync(dbeta, 0, (size_t)C * 4, st));
-  if (rows == 0) return PWA_OK;
-  return dtype == PWA_F32 ? ln_dispatch<float>(false, dy, x, gamma, mean, rstd, dres, dx, nullptr, dgamma, dbeta, rows, C, 0.f, st)
-                          : ln_dispatch<__nv_bfloat16>(false, dy, x, gamma, mean, rstd, dres, dx, nullptr, dgamma, dbeta, rows, C, 0.f, st);
+  return pwa_ln_bwd2(dy, x, gamma, mean, rstd, dres, dx, dgamma, dbeta, nullptr, nullptr, rows, C, dtype, stream);
 }

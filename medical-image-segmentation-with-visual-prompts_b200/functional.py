@@ -283,7 +283,7 @@ def prompted_window_attention(q, k, v, kp, vp, th, tw, td, tok, ids, heads: int,
 # ------------------------------------------------------------------------------------------------
 class _AddLayerNorm(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps):
+    def forward(ctx, x, res, gamma, beta, eps, bias_of_x=None, bias_of_res=None):
         x = x.contiguous()
         Cc = x.shape[-1]
         rows = x.numel() // Cc
@@ -304,6 +304,8 @@ class _AddLayerNorm(torch.autograd.Function):
         ctx.save_for_backward(normed, g32, mean, rstd)
         ctx.has_res = res is not None
         ctx.param_dtypes = (gamma.dtype, beta.dtype)
+        # bias parameters whose gradients are column sums this backward produces anyway (see include/pwa.h: pwa_ln_bwd2)
+        ctx.bias_dtypes = (None if bias_of_x is None else bias_of_x.dtype, None if bias_of_res is None else bias_of_res.dtype)
         if res is None:
             return y
         return s, y
@@ -322,13 +324,17 @@ class _AddLayerNorm(torch.autograd.Function):
         dx = torch.empty_like(normed)
         dg = torch.empty(Cc, dtype=torch.float32, device=normed.device)
         db = torch.empty(Cc, dtype=torch.float32, device=normed.device)
+        bx_dt, br_dt = ctx.bias_dtypes
+        dbx = torch.empty(Cc, dtype=torch.float32, device=normed.device) if bx_dt is not None else None
+        dbr = torch.empty(Cc, dtype=torch.float32, device=normed.device) if br_dt is not None and ds is not None else None
         nbytes = (3 if ds is None else 4) * normed.numel() * normed.element_size()
         with torch.cuda.device(normed.device), _timed("ln_bwd", 1, float(nbytes), normed):
-            rc = _lib.lib.pwa_ln_bwd(_ptr(dy), _ptr(normed), _ptr(g32), _ptr(mean), _ptr(rstd), _ptr(ds), _ptr(dx), _ptr(dg),
-                                     _ptr(db), rows, Cc, _dtype_code(normed), _stream(normed))
+            rc = _lib.lib.pwa_ln_bwd2(_ptr(dy), _ptr(normed), _ptr(g32), _ptr(mean), _ptr(rstd), _ptr(ds), _ptr(dx), _ptr(dg),
+                                      _ptr(db), _ptr(dbr), _ptr(dbx), rows, Cc, _dtype_code(normed), _stream(normed))
         _lib.check(rc, "pwa_ln_bwd")
         gd, bd = ctx.param_dtypes
-        return dx, (dx if ctx.has_res else None), dg.to(gd), db.to(bd), None
+        return (dx, (dx if ctx.has_res else None), dg.to(gd), db.to(bd), None,
+                None if dbx is None else dbx.to(bx_dt), None if dbr is None else dbr.to(br_dt))
 
 
 def layer_norm(x, gamma, beta, eps: float = 1e-6):
@@ -337,10 +343,13 @@ def layer_norm(x, gamma, beta, eps: float = 1e-6):
     return _AddLayerNorm.apply(x, None, gamma, beta, eps)
 
 
-def add_layer_norm(x, res, gamma, beta, eps: float = 1e-6):
-    """(s, y) with s = x + res and y = LayerNorm(s): the residual add of swin_block.py:222 fused into mlp_norm."""
+def add_layer_norm(x, res, gamma, beta, eps: float = 1e-6, bias_of_x=None, bias_of_res=None):
+    """(s, y) with s = x + res and y = LayerNorm(s): the residual add of swin_block.py:222 fused into mlp_norm.
+    bias_of_x / bias_of_res: optional Linear bias parameters whose gradients equal the column sums of d(x) and of
+    d(s) respectively (x = Linear(..) + bias_of_x; s is only ever added to Linear(..) + bias_of_res downstream): the
+    backward kernel produces them on the fly, and the Linears are then called with bias_grad=False."""
     _require_cuda(x, res, gamma, beta)
-    return _AddLayerNorm.apply(x, res, gamma, beta, eps)
+    return _AddLayerNorm.apply(x, res, gamma, beta, eps, bias_of_x, bias_of_res)
 
 
 def layer_norm_supported(C: int) -> bool:
@@ -499,7 +508,7 @@ class _MultiLinear(torch.autograd.Function):
     """y = x @ cat(weights)^T (+ bias): several nn.Linear weights that share an input, as ONE GEMM."""
 
     @staticmethod
-    def forward(ctx, x, bias, lowp, *weights):
+    def forward(ctx, x, bias, lowp, bias_grad, *weights):
         # `lowp`: the same weights already concatenated and cast to x.dtype (one cat + one cast per block instead
         # of two kernels per Linear); the fp32 master weights stay the autograd inputs
         w = lowp if lowp is not None else (weights[0] if len(weights) == 1 else torch.cat(weights, dim=0)).detach().to(x.dtype)
@@ -510,7 +519,7 @@ class _MultiLinear(torch.autograd.Function):
             y = torch.mm(x2, w.t())
         ctx.save_for_backward(x2, w)
         ctx.meta = (x.shape, [wt.shape[0] for wt in weights], [wt.dtype for wt in weights],
-                    None if bias is None else bias.dtype)
+                    None if (bias is None or not bias_grad) else bias.dtype)
         return y.reshape(*x.shape[:-1], w.shape[0])
 
     @staticmethod
@@ -521,15 +530,16 @@ class _MultiLinear(torch.autograd.Function):
         dx = torch.mm(dy2, w).reshape(xshape) if ctx.needs_input_grad[0] else None
         db = dy2.sum(dim=0, dtype=torch.float32).to(bdt) if bdt is not None and ctx.needs_input_grad[1] else None
         dws = [None] * len(rows)
-        if any(ctx.needs_input_grad[3:]):
+        if any(ctx.needs_input_grad[4:]):
             dw = _mm_f32(dy2.t(), x2)
             o = 0
             for i, r in enumerate(rows):
-                if ctx.needs_input_grad[3 + i]:
+                if ctx.needs_input_grad[4 + i]:
                     dws[i] = dw[o:o + r].to(wdts[i])
                 o += r
-        return (dx, db, None, *dws)
+        return (dx, db, None, None, *dws)
 
 
-def multi_linear(x, bias, *weights, lowp=None):
-    return _MultiLinear.apply(x, bias, lowp, *weights)
+def multi_linear(x, bias, *weights, lowp=None, bias_grad=True):
+    """bias_grad=False: the bias gradient is produced elsewhere (add_layer_norm's fused column sums)."""
+    return _MultiLinear.apply(x, bias, lowp, bias_grad, *weights)

@@ -71,3 +71,31 @@ class GraphedStep:
         if KernelStats.enabled:
             KernelStats.launches += self.launches_per_replay
         return self.loss
+
+
+class InputPrefetcher:
+    """Double-buffered host -> device input feed on a side stream: the pinned-host batch of step i+1 is copied while
+    step i computes.  `prefetch(t)` enqueues the copy, `get()` makes the current stream wait for the oldest pending
+    copy and returns the device buffer (valid until two more prefetches have been issued)."""
+
+    def __init__(self, example: torch.Tensor, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs = [torch.empty(example.shape, dtype=example.dtype, device=device) for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.head = self.tail = 0
+
+    def prefetch(self, host_batch: torch.Tensor):
+        k = self.head % 2
+        self.stream.wait_stream(torch.cuda.current_stream())    # the buffer's previous consumer has been enqueued
+        with torch.cuda.stream(self.stream):
+            self.bufs[k].copy_(host_batch, non_blocking=True)
+            self.events[k].record(self.stream)
+        self.head += 1
+
+    def get(self) -> torch.Tensor:
+        if self.tail >= self.head:
+            raise RuntimeError("InputPrefetcher.get() without a pending prefetch")
+        k = self.tail % 2
+        torch.cuda.current_stream().wait_event(self.events[k])
+        self.tail += 1
+        return self.bufs[k]

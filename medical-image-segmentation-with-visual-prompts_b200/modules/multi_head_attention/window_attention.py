@@ -43,7 +43,8 @@ class WindowAttention(nn.Module):
         self.impl = PF.IMPL_AUTO
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias: Optional[BiasTables] = None,
-                mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None, lowp: Optional[dict] = None):
+                mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None, lowp: Optional[dict] = None,
+                proj_bias_grad: bool = True):
         """q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
         appended to the keys/values of every window; pos_bias: BiasTables; mask: uint8 region ids [P,N]
         (mask[p,i,j] = ids[p,i]==ids[p,j]) or None; lowp: optional {'qkv','kv','proj'} weights already cast to the
@@ -72,5 +73,5 @@ class WindowAttention(nn.Module):
                 vp = PF.multi_linear(prompts, None, self.to_v.weight)
             o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok,
                                              mask, self.num_heads, pos_bias.ws, self.scale, self.impl)
-        o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'))
+        o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'), bias_grad=proj_bias_grad)
         return self.proj_drop(o)

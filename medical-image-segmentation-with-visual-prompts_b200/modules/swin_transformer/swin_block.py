@@ -165,9 +165,17 @@ class SwinTransformerBlock(nn.Module):
             tokens = PF.layer_norm(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
             prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6) \
                 if p is not None else None
+            # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway
+            # (d of the attention branch, and d of y which equals d of m: both only meet in y + m); the two Linears
+            # skip their own bias reductions.  Only valid without projection dropout between proj and the add.
+            fuse_db = not (self.training and self.attn.proj_drop.p > 0)
             a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                          prompts=prompts, lowp=lowp)
-            y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6)
+                          prompts=prompts, lowp=lowp, proj_bias_grad=not fuse_db)
+            y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
+                                     bias_of_x=self.attn.proj.bias if fuse_db else None,
+                                     bias_of_res=self.mlp.bias if fuse_db else None)
+            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=not fuse_db)
+            return y, m
         else:
             nw, nb = self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt)
             tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)

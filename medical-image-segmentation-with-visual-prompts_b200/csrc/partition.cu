@@ -15,9 +15,14 @@
 // whole D-lines, the token side moves runs of ww*wd*CT contiguous elements per window.
 // All traffic is 32-bit words (one fp32 or a pair of bf16 channels); bf16 needs a 2x2 in-register
 // transpose (PRMT) because x is contiguous along D and tokens along C.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pwa {
+
+int partition_tma_run(bool is_partition, const void* src, const void* src2, void* dst, int B, int C, const pwa_geom* g,
+                      const int32_t* lo, int eb, cudaStream_t st);   // partition_tma.cu
 
 struct PartParams {
   int B, C;
@@ -583,7 +588,15 @@ static int run(bool is_partition, const void* src, const void* src2, void* dst, 
   PartParams p;
   bool fast = false, vec = false;
   fill_params(p, B, C, g, use_crop_lo, eb, &fast, &vec);
-  // `use_crop_lo & 2` forces the generic kernel, `& 4` the word kernel (tests cross-check the three paths)
+  // `use_crop_lo & 2` forces the generic kernel, `& 4` the word kernel, `& 8` the vector kernel (tests cross-check
+  // the paths); otherwise the TMA-staged kernel (partition_tma.cu) takes every shape inside its envelope
+  cudaStream_t st0 = (cudaStream_t)stream;
+  static const bool no_tma = getenv("PWA_NO_TMA") != nullptr;
+  if (!(use_crop_lo & (2 | 4 | 8)) && !no_tma) {
+    const int32_t* lo = (use_crop_lo & 1) ? g->crop_lo : g->data_lo;
+    const int rc = partition_tma_run(is_partition, src, src2, dst, B, C, g, lo, eb, st0);
+    if (rc != PWA_ERR_UNSUPPORTED) return rc;
+  }
   if (use_crop_lo & 2) fast = vec = false;
   if (use_crop_lo & 4) vec = false;
   if (((uintptr_t)src | (uintptr_t)src2 | (uintptr_t)dst) & 3) fast = false;   // staged paths move aligned 32-bit words

@@ -78,23 +78,29 @@ def _ptr(t: Optional[torch.Tensor]):
 # ------------------------------------------------------------------------------------------------
 # (a) partition / reverse
 # ------------------------------------------------------------------------------------------------
+def _force_bits(force_generic, force_word, force_vec):
+    """Kernel selection bits of pwa_partition / pwa_reverse (tests cross-check the paths): default = TMA-staged kernel
+    when the shape is inside its envelope, else vector -> word -> generic."""
+    return (2 if force_generic else 0) | (4 if force_word else 0) | (8 if force_vec else 0)
+
+
 def _partition_raw(x: torch.Tensor, geom: Geometry, crop_lo: int, force_generic: bool = False,
-                   force_word: bool = False) -> torch.Tensor:
+                   force_word: bool = False, force_vec: bool = False) -> torch.Tensor:
     B, Cc = x.shape[:2]
     out = torch.empty((B, geom.P, geom.N, Cc), dtype=x.dtype, device=x.device)
     with torch.cuda.device(x.device), _timed("partition", 1, 2.0 * out.numel() * out.element_size(), x):
-        rc = _lib.lib.pwa_partition(_ptr(x), _ptr(out), B, Cc, geom.ref(), crop_lo | (2 if force_generic else 0) | (4 if force_word else 0),
+        rc = _lib.lib.pwa_partition(_ptr(x), _ptr(out), B, Cc, geom.ref(), crop_lo | _force_bits(force_generic, force_word, force_vec),
                                     _dtype_code(x), _stream(x))
     _lib.check(rc, "pwa_partition")
     return out
 
 
 def _reverse_raw(tok: torch.Tensor, geom: Geometry, crop_lo: int, force_generic: bool = False,
-                 force_word: bool = False) -> torch.Tensor:
+                 force_word: bool = False, force_vec: bool = False) -> torch.Tensor:
     B, _, _, Cc = tok.shape
     out = torch.empty((B, Cc, *geom.dims), dtype=tok.dtype, device=tok.device)
     with torch.cuda.device(tok.device), _timed("reverse", 1, 2.0 * tok.numel() * tok.element_size(), tok):
-        rc = _lib.lib.pwa_reverse(_ptr(tok), _ptr(out), B, Cc, geom.ref(), crop_lo | (2 if force_generic else 0) | (4 if force_word else 0),
+        rc = _lib.lib.pwa_reverse(_ptr(tok), _ptr(out), B, Cc, geom.ref(), crop_lo | _force_bits(force_generic, force_word, force_vec),
                                   _dtype_code(tok), _stream(tok))
     _lib.check(rc, "pwa_reverse")
     return out

@@ -38,6 +38,7 @@ def test_partition_reverse_bit_exact(dims, ws, shift_cfg, dtype, C):
     assert torch.equal(got.cpu(), exp)
     assert torch.equal(PF._partition_raw(xd, g, 0, force_generic=True).cpu(), exp)
     assert torch.equal(PF._partition_raw(xd, g, 0, force_word=True).cpu(), exp)
+    assert torch.equal(PF._partition_raw(xd, g, 0, force_vec=True).cpu(), exp)
     # output side: window reverse + roll back + crop (crop offsets), and the two adjoints
     t = torch.randn(2, g.P, g.N, C, generator=gen).to(dtype)
     exp_r = R.reverse_tokens(t.float(), dims, ws, shift, pads).to(dtype)
@@ -45,6 +46,11 @@ def test_partition_reverse_bit_exact(dims, ws, shift_cfg, dtype, C):
     assert torch.equal(PF._reverse_raw(td, g, 1).cpu(), exp_r)
     assert torch.equal(PF._reverse_raw(td, g, 1, force_generic=True).cpu(), exp_r)
     assert torch.equal(PF._reverse_raw(td, g, 1, force_word=True).cpu(), exp_r)
+    assert torch.equal(PF._reverse_raw(td, g, 1, force_vec=True).cpu(), exp_r)
+    # fused residual add (fp32 sum, rounded once) through the default path
+    t2 = torch.randn(2, g.P, g.N, C, generator=gen).to(dtype)
+    exp_ra = R.reverse_tokens((t.float() + t2.float()).to(dtype).float(), dims, ws, shift, pads).to(dtype)
+    assert torch.equal(PF.reverse_add_tokens(td, t2.to(DEV), g).cpu(), exp_ra)
     idx0 = torch.from_numpy(R.gather_index(dims, ws, shift, pads)).reshape(-1)
     adj = torch.zeros(2, C, dims[0] * dims[1] * dims[2] + 1, dtype=dtype)
     adj[:, :, idx0] = t.permute(0, 3, 1, 2).reshape(2, C, -1)       # unique targets except the -1 slot
@@ -65,10 +71,12 @@ def test_partition_full_size_round_trip(dims, C, B, dtype):
         tok = PF._partition_raw(x, g, 0)
         assert torch.equal(tok, PF._partition_raw(x, g, 0, force_generic=True))
         assert torch.equal(tok, PF._partition_raw(x, g, 0, force_word=True))
+        assert torch.equal(tok, PF._partition_raw(x, g, 0, force_vec=True))
         back = PF._reverse_raw(tok, g, 0)
         assert torch.equal(back, x)
         assert torch.equal(back, PF._reverse_raw(tok, g, 0, force_generic=True))
         assert torch.equal(back, PF._reverse_raw(tok, g, 0, force_word=True))
+        assert torch.equal(back, PF._reverse_raw(tok, g, 0, force_vec=True))
         # checksum of checksums: a permutation (+ zero padding) preserves the multiset of values
         assert torch.equal(tok.float().sum(dim=(1, 2)).sum(), tok.float().sum(dim=(1, 2)).sum())
         assert tok.count_nonzero() == x.count_nonzero()

@@ -200,16 +200,19 @@ def run_ours(args):
     graphed = None
     if not args.no_graph:
         from pwa_b200.graphs import GraphedStep
-        graphed = GraphedStep(lambda x: encoder_step(model, plist, x), [xdev[0].clone().requires_grad_(True)], params)
+        graphed = GraphedStep(lambda x: encoder_step(model, plist, x), [xdev[0].clone().requires_grad_(True)], params,
+                              flat_grads=world > 1)
 
     def run_step(x_src):
         if graphed is not None:
             loss = graphed(x_src)                     # copy into the static input (H2D or D2D) + one graph launch
+            if world > 1:
+                graphed.allreduce_flat()              # ONE in-place NCCL all-reduce of the flat gradient buffer
         else:
             zero()
             loss = encoder_step(model, plist, x_src.to(dev, non_blocking=True).clone().requires_grad_(True))
-        if world > 1:
-            allreduce_grads(params, world)
+            if world > 1:
+                allreduce_grads(params, world)
         return loss
 
     def step_resident(i):

@@ -22,15 +22,34 @@ from .functional import KernelStats
 
 class GraphedStep:
     def __init__(self, step_fn: Callable[..., torch.Tensor], example_inputs: Sequence[torch.Tensor],
-                 params: Iterable[torch.nn.Parameter], warmup: int = 3):
+                 params: Iterable[torch.nn.Parameter], warmup: int = 3, flat_grads: bool = False):
         """step_fn(*inputs) must run forward AND backward and return a (scalar) loss tensor; it is called `warmup`
         times eagerly on a side stream (lazy initialisation: cuBLAS handles, kernel attributes, cached index maps),
-        then once more under capture.  Inputs that require grad get a static .grad too (`input_grads`)."""
+        then once more under capture.  Inputs that require grad get a static .grad too (`input_grads`).
+        flat_grads=True makes every parameter's .grad a view into ONE flat fp32 buffer (`flat_grad`, zeroed inside the
+        graph at the start of each step), so that the data-parallel exchange is a single in-place all-reduce of that
+        buffer with no gather / scatter copies (`allreduce_flat`)."""
         if not example_inputs or not all(t.is_cuda for t in example_inputs):
             raise RuntimeError("GraphedStep: CUDA tensors only (pwa_b200 has no CPU path)")
         self.params: List[torch.nn.Parameter] = [p for p in params]
         self.static_inputs = [t.detach().clone().requires_grad_(t.requires_grad) for t in example_inputs]
         self._step_fn = step_fn
+        self.flat_grad = None
+        if flat_grads:
+            if any(p.dtype != torch.float32 for p in self.params):
+                raise RuntimeError("GraphedStep(flat_grads=True) needs fp32 master parameters")
+            self.flat_grad = torch.zeros(sum(p.numel() for p in self.params), dtype=torch.float32,
+                                         device=self.static_inputs[0].device)
+            o = 0
+            self._grad_views = []
+            for p in self.params:
+                self._grad_views.append(self.flat_grad[o:o + p.numel()].view_as(p))
+                o += p.numel()
+            inner = step_fn
+
+            def step_fn(*inputs):
+                self.flat_grad.zero_()
+                return inner(*inputs)
         # CUDA events cannot be recorded inside a capture; launches are counted during the capture pass
         saved = (KernelStats.enabled, KernelStats.timing, KernelStats.launches)
         KernelStats.enabled, KernelStats.timing = True, False
@@ -53,10 +72,22 @@ class GraphedStep:
             KernelStats.enabled, KernelStats.timing, KernelStats.launches = saved
 
     def _zero(self):
-        for p in self.params:
-            p.grad = None
+        if self.flat_grad is not None:
+            for p, v in zip(self.params, self._grad_views):
+                p.grad = v                      # autograd accumulates in place into the flat buffer
+        else:
+            for p in self.params:
+                p.grad = None
         for t in self.static_inputs:
             t.grad = None
+
+    def allreduce_flat(self, group=None):
+        """Average the flat gradient buffer over the data-parallel group: one NCCL all-reduce, one scale kernel."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        if world > 1:
+            dist.all_reduce(self.flat_grad, group=group)
+            self.flat_grad.div_(world)
 
     @property
     def input_grads(self):

@@ -109,11 +109,16 @@ typedef struct pwa_attn_shape {
   int32_t B, P, C, heads, I;   /* I = number of prompt tokens (0 = none)           */
   int32_t ws[3];               /* N = ws[0]*ws[1]*ws[2]                            */
   float scale;                 /* head_dim ** -0.5  (window_attention.py:25)       */
-  float p_drop;                /* attention dropout probability (0 in eval)        */
-  uint64_t seed, offset;       /* Philox key/counter taken from torch's generator  */
+  float p_drop;                /* attention dropout probability (0 in eval), applied in steps of 1/256 after the
+                                  softmax (window_attention.py:57); the forward and backward calls of one step must
+                                  see the same seed words.  Runs on the fp32-math kernels (impl 0 / 1).            */
+  uint64_t seed, offset;       /* host seed words (e.g. torch's generator seed / offset)                          */
   int32_t ld_qkv;              /* row stride (elements) of q,k,v and dq,dk,dv; 0 = C.  3*C when q|k|v are the
                                   column blocks of ONE fused projection output [B][P][N][3C]            */
   int32_t ld_p;                /* row stride of kp, vp; 0 = C (2*C for a fused [B][I][2C] projection)  */
+  const void* seed_dev;        /* optional DEVICE pointer to two uint32 seed words that replace seed/offset: the
+                                  words can be refreshed by a device-side RNG op every step, which keeps a captured
+                                  CUDA graph of the step valid (host scalars would be frozen into the graph)      */
 } pwa_attn_shape;
 
 /* q,k,v [B][P][N][C]; kp,vp [B][I][C] (NULL when I == 0): keys/values of the prompt tokens,

@@ -27,6 +27,7 @@ class PwaAttnShape(C.Structure):
         ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("I", C.c_int32),
         ("ws", C.c_int32 * 3), ("scale", C.c_float), ("p_drop", C.c_float),
         ("seed", C.c_uint64), ("offset", C.c_uint64), ("ld_qkv", C.c_int32), ("ld_p", C.c_int32),
+        ("seed_dev", C.c_void_p),
     ]
 
 
@@ -54,6 +55,8 @@ def _load():
     lib.pwa_reverse_add.restype = i32
     lib.pwa_gather_rows.argtypes = [vp, vp, vp, vp, i32, C.c_int64, C.c_int64, i32, i32, vp]
     lib.pwa_gather_rows.restype = i32
+    lib.pwa_debug_fwd_timeline.argtypes = [vp, i32]
+    lib.pwa_debug_fwd_timeline.restype = i32
     lib.pwa_attn_tc_supported.argtypes = [sp, i32]
     lib.pwa_attn_fwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, sp, i32, i32, vp]
     lib.pwa_attn_bwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, vp] + [vp] * 3 + [f32p] * 7 + [sp, i32, i32, vp]

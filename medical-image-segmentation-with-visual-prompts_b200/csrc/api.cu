@@ -13,9 +13,18 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
   PWA_CHECK_ARG(s->C % s->heads == 0, "WindowAttention: The dimension is not compatible with the number of heads!");
   PWA_CHECK_ARG(s->ws[0] > 0 && s->ws[1] > 0 && s->ws[2] > 0 && s->ws[2] <= 8, "%s: window (%d,%d,%d) unsupported (need wd <= 8)",
                 who, s->ws[0], s->ws[1], s->ws[2]);
-  if (s->p_drop != 0.f) {
-    set_error("%s: attention dropout inside the fused kernel is not implemented yet (p_drop=%g)", who, (double)s->p_drop);
-    return PWA_ERR_UNSUPPORTED;
+  PWA_CHECK_ARG(s->p_drop >= 0.f && s->p_drop < 1.f, "%s: p_drop=%g outside [0, 1)", who, (double)s->p_drop);
+  {
+    // dropout probability in steps of 1/256 (0.1 -> 26/256 = 0.1016); the kept entries are scaled by the exact inverse
+    // of the QUANTISED keep rate, so the estimator stays unbiased
+    int t = (int)(s->p_drop * 256.f + 0.5f);
+    if (t > 255) t = 255;
+    if (s->p_drop > 0.f && t == 0) t = 1;
+    p.drop_thresh = (uint32_t)t;
+    p.inv_keep = 256.f / (float)(256 - t);
+    p.drop_seed = (const uint32_t*)s->seed_dev;
+    p.seed_host[0] = (uint32_t)(s->seed ^ (s->offset << 32)) ^ (uint32_t)(s->offset >> 7);
+    p.seed_host[1] = (uint32_t)(s->seed >> 32) ^ (uint32_t)s->offset * 0x9E3779B1u;
   }
   p.B = s->B; p.P = s->P; p.C = s->C; p.heads = s->heads; p.I = s->I;
   p.wh = s->ws[0]; p.ww = s->ws[1]; p.wd = s->ws[2];
@@ -33,6 +42,15 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
 }  // namespace pwa
 
 using namespace pwa;
+
+static void* g_fwd_timeline = nullptr;
+
+/* test infrastructure: copy the forward kernel's debug timeline (PWA_TIMELINE=1) to the host; returns bytes copied */
+extern "C" int pwa_debug_fwd_timeline(void* host_dst, int bytes) {
+  if (!g_fwd_timeline || bytes > (1 << 20)) return 0;
+  if (cudaMemcpy(host_dst, g_fwd_timeline, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return bytes;
+}
 
 extern "C" int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype) {
   AttnParams p = {};
@@ -53,7 +71,15 @@ extern "C" int pwa_attn_fwd(const void* q, const void* k, const void* v, const v
   p.th = th; p.tw = tw; p.td = td; p.tok = tok; p.ids = ids;
   p.out = out; p.lse = lse;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tc_ok = attn_tc_supported(p, dtype);
+  if (p.debug) {   // PWA_TIMELINE=1 (test infrastructure): CTA 0 of the forward kernel writes clock64 stamps here
+    static void* tl = nullptr;
+    if (!tl) PWA_CUDA_OK(cudaMalloc(&tl, 1 << 20));
+    PWA_CUDA_OK(cudaMemsetAsync(tl, 0, 1 << 20, st));
+    p.delta = (float*)tl;
+    g_fwd_timeline = tl;
+  }
+  // (attention dropout currently runs on the fp32-math kernels only)
+  const bool tc_ok = attn_tc_supported(p, dtype) && p.drop_thresh == 0;
   if (impl == 2 && !tc_ok) {
     set_error("pwa_attn_fwd: tcgen05 kernel does not support this shape/dtype");
     return PWA_ERR_UNSUPPORTED;
@@ -89,7 +115,7 @@ extern "C" int pwa_attn_bwd(const void* q, const void* k, const void* v, const v
     PWA_CUDA_OK(cudaMemsetAsync(dkp, 0, (size_t)p.B * p.I * p.C * 4, st));
     PWA_CUDA_OK(cudaMemsetAsync(dvp, 0, (size_t)p.B * p.I * p.C * 4, st));
   }
-  const bool tc_ok = attn_tc_bwd_supported(p, dtype);
+  const bool tc_ok = attn_tc_bwd_supported(p, dtype) && p.drop_thresh == 0;
   if (impl == 2 && !tc_ok) {
     set_error("pwa_attn_bwd: tcgen05 kernel does not support this shape/dtype");
     return PWA_ERR_UNSUPPORTED;

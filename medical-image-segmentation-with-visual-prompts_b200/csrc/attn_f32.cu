@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
   float* Vs = sm + L.b;
   const uint8_t* ids_s = (const uint8_t*)(sm + L.ids);
   const bool masked = p.ids != nullptr;
+  const bool drop = p.drop_thresh != 0;
+  const uint32_t seed0 = p.drop_seed ? p.drop_seed[0] : p.seed_host[0], seed1 = p.drop_seed ? p.drop_seed[1] : p.seed_host[1];
 
   for (int i = tid; i < p.NK * DH; i += kThreads) {
     int j = i / DH, d = i - j * DH;
@@ -107,6 +109,8 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
     }
     const int id_ = n % p.wd, iw = (n / p.wd) % p.ww, ih = n / (p.wd * p.ww);
     const int rid = masked ? ids_s[n] : 0;
+    const uint32_t rstate = drop ? drop_row_state(seed0, seed1, bw, p.heads, head, (p.N + 1) / 2, n) : 0u;
+    uint32_t dbits = 0;
     float m = -1e30f, l = 0.f;
     auto step = [&](int j, float bias, bool keep) {
       float s = bias;
@@ -122,7 +126,11 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
         m = s;
       }
       float pr = __expf(s - m);
-      l += pr;
+      l += pr;                                            // the softmax denominator is not affected by dropout
+      if (drop) {
+        if ((j & 1) == 0 || j == p.N) dbits = drop_block_bits(rstate, (uint32_t)j);
+        if (!drop_keep(dbits, (uint32_t)n, (uint32_t)j, p.drop_thresh)) pr = 0.f;   // (kept ones are scaled once, below)
+      }
       const float* vr = Vs + j * DH;
 #pragma unroll
       for (int d = 0; d < DH; ++d) o[d] = fmaf(pr, vr[d], o[d]);
@@ -140,7 +148,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
     }
     for (int i = 0; i < p.I; ++i) step(p.N + i, sm[L.tok + i], true);
 
-    const float inv = 1.f / l;
+    const float inv = (drop ? p.inv_keep : 1.f) / l;
     T* og = (T*)p.out + row * p.C + head * DH;
 #pragma unroll
     for (int d = 0; d < DH; ++d) og[d] = from_f32<T>(o[d] * inv);
@@ -162,6 +170,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
   float* Vs = sm + L.b;
   const uint8_t* ids_s = (const uint8_t*)(sm + L.ids);
   const bool masked = p.ids != nullptr;
+  const bool drop = p.drop_thresh != 0;
+  const uint32_t seed0 = p.drop_seed ? p.drop_seed[0] : p.seed_host[0], seed1 = p.drop_seed ? p.drop_seed[1] : p.seed_host[1];
 
   for (int i = tid; i < p.NK * DH; i += kThreads) {
     int j = i / DH, d = i - j * DH;
@@ -195,6 +205,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
     if (live) p.delta[stat] = delta;
     const int id_ = nn % p.wd, iw = (nn / p.wd) % p.ww, ih = nn / (p.wd * p.ww);
     const int rid = masked ? ids_s[nn] : 0;
+    const uint32_t rstate = drop ? drop_row_state(seed0, seed1, bw, p.heads, head, (p.N + 1) / 2, nn) : 0u;
+    uint32_t dbits = 0;
 
     auto grad = [&](int j, float bias, bool keep) -> float {
       float s = bias;
@@ -207,6 +219,10 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
       float dp = 0.f;
 #pragma unroll
       for (int d = 0; d < DH; ++d) dp = fmaf(dor[d], vr[d], dp);
+      if (drop) {   // d P = d P_dropped * mask / keep_rate ; delta = rowsum(dO * O) is unchanged
+        if ((j & 1) == 0 || j == p.N) dbits = drop_block_bits(rstate, (uint32_t)j);
+        dp = drop_keep(dbits, (uint32_t)nn, (uint32_t)j, p.drop_thresh) ? dp * p.inv_keep : 0.f;
+      }
       const float g = keep ? pr * (dp - delta) : 0.f;  // d logits / d (q.k*scale + bias) = mask
 #pragma unroll
       for (int d = 0; d < DH; ++d) dqr[d] = fmaf(g, kr[d], dqr[d]);
@@ -273,6 +289,8 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_f32_kernel(AttnParams p
   float* dOs = sm + L.b;
   const uint8_t* ids_s = (const uint8_t*)(sm + L.ids);
   const bool masked = p.ids != nullptr;
+  const bool drop = p.drop_thresh != 0;
+  const uint32_t seed0 = p.drop_seed ? p.drop_seed[0] : p.seed_host[0], seed1 = p.drop_seed ? p.drop_seed[1] : p.seed_host[1];
 
   for (int i = tid; i < p.N * DH; i += kThreads) {
     int n = i / DH, d = i - n * DH;
@@ -303,6 +321,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_f32_kernel(AttnParams p
     const int jd = j % p.wd, jw = (j / p.wd) % p.ww, jh = content ? j / (p.wd * p.ww) : 0;
     const int cid = (masked && content) ? ids_s[j] : -1;
     const float tokb = content ? 0.f : sm[L.tok + (j - p.N)];
+    uint32_t dbits = 0;
     int n = 0;
     for (int ih = 0; ih < p.wh; ++ih) {
       const float bh = content ? sm[L.th + ih * p.wh + jh] : tokb;
@@ -320,10 +339,16 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_f32_kernel(AttnParams p
           const float pr = __expf(s - sm[L.lse + n]);
           float dp = 0.f;
 #pragma unroll
-          for (int d = 0; d < DH; ++d) {
-            dvr[d] = fmaf(pr, dor[d], dvr[d]);
-            dp = fmaf(dor[d], vr[d], dp);
+          for (int d = 0; d < DH; ++d) dp = fmaf(dor[d], vr[d], dp);
+          float prd = pr;
+          if (drop) {
+            if ((n & 1) == 0) dbits = drop_block_bits(drop_row_state(seed0, seed1, bw, p.heads, head, (p.N + 1) / 2, n), (uint32_t)j);
+            const float kf = drop_keep(dbits, (uint32_t)n, (uint32_t)j, p.drop_thresh) ? p.inv_keep : 0.f;
+            prd *= kf;
+            dp *= kf;
           }
+#pragma unroll
+          for (int d = 0; d < DH; ++d) dvr[d] = fmaf(prd, dor[d], dvr[d]);
           const float g = keep ? pr * (dp - sm[L.delta + n]) : 0.f;
 #pragma unroll
           for (int d = 0; d < DH; ++d) dkr[d] = fmaf(g, qr[d], dkr[d]);

@@ -210,6 +210,11 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   const int n_pairs = p.B * p.P;
   const int stride = gridDim.x / p.heads;
 
+  long long* tl = reinterpret_cast<long long*>(p.delta);
+  int tli = 0;
+  const bool rec = p.debug && p.delta != nullptr && blockIdx.x == 0 && tid == 0;
+#define STAMP(tag) do { if (rec && tli < 2000) { tl[2 * tli] = clock64(); tl[2 * tli + 1] = (tag); ++tli; } } while (0)
+
   // S = Q'.K'^T for (query tile mt, key block kb); single thread
   auto issue_s = [&](int mt, int kb) {
     tc_fence_after();
@@ -228,6 +233,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
 
   for (int bw = blockIdx.x / p.heads; bw < n_pairs; bw += stride) {
     const int b = bw / p.P, win = bw - b * p.P;
+    STAMP(1);
     // ---- stage this (window, head): Q, K (content + prompt rows), [V | 1], region ids ----
     __nv_bfloat16 extra[4];
     float qn2[2];
@@ -300,6 +306,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
     }
     // (the __syncthreads_or also orders the selector table writes before their first use)
     const bool exact = __syncthreads_or(loose) != 0;
+    STAMP(2);
 
     for (int mt = 0; mt < 2; ++mt) {
       const int rown = mt * kRows + tid;
@@ -341,11 +348,13 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
 
       for (int kb = 0; kb < n_kb; ++kb) {
         const int nk = kb < 2 ? 128 : p.I;
+        STAMP(10 + mt * 3 + kb);
         if (tid == 0) issue_s(mt, kb);
         __syncwarp();
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
+        STAMP(100);
 
         // ---- P = exp2(S*c2 - mb), packed bf16 back into TMEM ----
         const bool do_mask = MASKED && kb < 2;
@@ -376,8 +385,10 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
           tmem_st16(trow + c * 16, pk);
         }
         tmem_wait_st();
+        STAMP(101);
         tc_fence_before();
         __syncthreads();
+        STAMP(102);
 
         // ---- O_blk = P.[V | 1] ----
         if (tid == 0) {
@@ -392,6 +403,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         mbar_wait(&bar, phase);
         phase ^= 1;
         tc_fence_after();
+        STAMP(103);
 #pragma unroll
         for (int dq = 0; dq < DHP / 16; ++dq) {
           uint32_t o[16];
@@ -403,6 +415,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         }
         tc_fence_before();
         __syncthreads();   // everyone has drained O / P before the next S MMA overwrites the columns
+        STAMP(104);
       }
 
       // ---- epilogue: normalise, write bf16 output row slice and log-sum-exp ----
@@ -424,6 +437,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       p.lse[((size_t)bw * p.heads + head) * kN + rown] = (mb + __log2f(l_run)) * 0.6931471805599453f;
     }
   }
+#undef STAMP
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, kTmemCols);

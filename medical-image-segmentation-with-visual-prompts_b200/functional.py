@@ -219,18 +219,19 @@ def gather_rows(a: torch.Tensor, b: Optional[torch.Tensor], rowmap) -> torch.Ten
 IMPL_AUTO, IMPL_F32, IMPL_TC = 0, 1, 2
 
 
-def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0):
+def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0, seed_dev=None):
     s = _lib.PwaAttnShape()
     s.B, s.P, s.C, s.heads, s.I = B, P, Cc, heads, I
     s.ld_qkv, s.ld_p = ld_qkv, ld_p
     s.ws[0], s.ws[1], s.ws[2] = ws
     s.scale, s.p_drop, s.seed, s.offset = float(scale), float(p_drop), int(seed), int(offset)
+    s.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
     return s
 
 
 class _WindowAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, kp, vp, th, tw, td, tok, ids, heads, ws, scale, impl):
+    def forward(ctx, q, k, v, kp, vp, th, tw, td, tok, ids, heads, ws, scale, impl, p_drop=0.0, seed=None):
         q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
         B, P, N, Cc = q.shape
         I = 0 if kp is None else kp.shape[1]
@@ -239,20 +240,20 @@ class _WindowAttention(torch.autograd.Function):
         th, tw, td = th.contiguous().float(), tw.contiguous().float(), td.contiguous().float()
         out = torch.empty_like(q)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=q.device)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed)
         with torch.cuda.device(q.device), _timed("attn_fwd", 1, 4.0 * B * P * N * (N + I) * Cc, q):
             rc = _lib.lib.pwa_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(kp), _ptr(vp), _ptr(th), _ptr(tw), _ptr(td),
                                        _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), C.byref(s), _dtype_code(q), impl,
                                        _stream(q))
         _lib.check(rc, "pwa_attn_fwd")
-        ctx.save_for_backward(q, k, v, kp, vp, th, tw, td, tok, ids, out, lse)
-        ctx.meta = (heads, tuple(ws), scale, impl, I)
+        ctx.save_for_backward(q, k, v, kp, vp, th, tw, td, tok, ids, out, lse, seed)
+        ctx.meta = (heads, tuple(ws), scale, impl, I, p_drop)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        q, k, v, kp, vp, th, tw, td, tok, ids, out, lse = ctx.saved_tensors
-        heads, ws, scale, impl, I = ctx.meta
+        q, k, v, kp, vp, th, tw, td, tok, ids, out, lse, seed = ctx.saved_tensors
+        heads, ws, scale, impl, I, p_drop = ctx.meta
         B, P, N, Cc = q.shape
         dout = dout.contiguous()
         dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
@@ -262,7 +263,7 @@ class _WindowAttention(torch.autograd.Function):
         dth, dtw, dtd = torch.empty_like(th), torch.empty_like(tw), torch.empty_like(td)
         dtok = torch.empty_like(tok) if I else None
         delta = torch.empty_like(lse)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed)
         with torch.cuda.device(q.device), _timed("attn_bwd", 2, 8.0 * B * P * N * (N + I) * Cc, q):
             rc = _lib.lib.pwa_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(kp), _ptr(vp), _ptr(th), _ptr(tw), _ptr(td),
                                        _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), _ptr(dout), _ptr(dq), _ptr(dk),
@@ -271,17 +272,19 @@ class _WindowAttention(torch.autograd.Function):
         _lib.check(rc, "pwa_attn_bwd")
         if I:
             dkp, dvp = dkp.to(q.dtype), dvp.to(q.dtype)
-        return dq, dk, dv, dkp, dvp, dth, dtw, dtd, dtok, None, None, None, None, None
+        return dq, dk, dv, dkp, dvp, dth, dtw, dtd, dtok, None, None, None, None, None, None, None
 
 
 def prompted_window_attention(q, k, v, kp, vp, th, tw, td, tok, ids, heads: int, ws: Sequence[int], scale: float,
-                              impl: int = IMPL_AUTO) -> torch.Tensor:
+                              impl: int = IMPL_AUTO, p_drop: float = 0.0, seed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q,k,v [B,P,N,C]; kp,vp [B,I,C] or None; th/tw/td [h,w,w] + tok [h,I] fp32 bias tables;
     ids uint8 [P,N] or None.  Returns [B,P,N,C].  See include/pwa.h: pwa_attn_fwd."""
     _require_cuda(q, k, v, kp, vp, th, tw, td, tok, ids)
     if q.shape[-1] % heads != 0:
         raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
-    return _WindowAttention.apply(q, k, v, kp, vp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl)
+    if p_drop > 0 and seed is None:
+        seed = new_dropout_seed(q.device)
+    return _WindowAttention.apply(q, k, v, kp, vp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl, float(p_drop), seed)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -431,7 +434,7 @@ def bias_tables(enc_h, enc_w, enc_d, wc_h, wc_w, wc_d, enc_tok, w_tok, ws):
 # ------------------------------------------------------------------------------------------------
 class _WindowAttentionPacked(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, kvp, th, tw, td, tok, ids, heads, ws, scale, impl):
+    def forward(ctx, qkv, kvp, th, tw, td, tok, ids, heads, ws, scale, impl, p_drop=0.0, seed=None):
         qkv = qkv.contiguous()
         B, P, N, C3 = qkv.shape
         Cc = C3 // 3
@@ -442,7 +445,7 @@ class _WindowAttentionPacked(torch.autograd.Function):
         th, tw, td = th.contiguous().float(), tw.contiguous().float(), td.contiguous().float()
         out = torch.empty((B, P, N, Cc), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=qkv.device)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, ld_qkv=C3, ld_p=2 * Cc)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed)
         q0 = qkv.data_ptr()
         p0 = 0 if kvp is None else kvp.data_ptr()
         vpp = C.c_void_p
@@ -451,14 +454,14 @@ class _WindowAttentionPacked(torch.autograd.Function):
                                        _ptr(th), _ptr(tw), _ptr(td), _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), C.byref(s),
                                        _dtype_code(qkv), impl, _stream(qkv))
         _lib.check(rc, "pwa_attn_fwd")
-        ctx.save_for_backward(qkv, kvp, th, tw, td, tok, ids, out, lse)
-        ctx.meta = (heads, tuple(ws), scale, impl, I)
+        ctx.save_for_backward(qkv, kvp, th, tw, td, tok, ids, out, lse, seed)
+        ctx.meta = (heads, tuple(ws), scale, impl, I, p_drop)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        qkv, kvp, th, tw, td, tok, ids, out, lse = ctx.saved_tensors
-        heads, ws, scale, impl, I = ctx.meta
+        qkv, kvp, th, tw, td, tok, ids, out, lse, seed = ctx.saved_tensors
+        heads, ws, scale, impl, I, p_drop = ctx.meta
         B, P, N, C3 = qkv.shape
         Cc = C3 // 3
         es = qkv.element_size()
@@ -469,7 +472,7 @@ class _WindowAttentionPacked(torch.autograd.Function):
         dth, dtw, dtd = torch.empty_like(th), torch.empty_like(tw), torch.empty_like(td)
         dtok = torch.empty_like(tok) if I else None
         delta = torch.empty_like(lse)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, ld_qkv=C3, ld_p=2 * Cc)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed)
         q0, d0 = qkv.data_ptr(), dqkv.data_ptr()
         p0 = 0 if kvp is None else kvp.data_ptr()
         vpp = C.c_void_p
@@ -485,16 +488,26 @@ class _WindowAttentionPacked(torch.autograd.Function):
         dkvp = None
         if I:
             dkvp = torch.cat([dkvp32[0], dkvp32[1]], dim=-1).to(qkv.dtype)          # [B,I,2C]
-        return dqkv, dkvp, dth, dtw, dtd, dtok, None, None, None, None, None
+        return dqkv, dkvp, dth, dtw, dtd, dtok, None, None, None, None, None, None, None
+
+
+def new_dropout_seed(device) -> torch.Tensor:
+    """Two 32-bit seed words ON THE DEVICE for one attention-dropout call (forward and backward share them).  Drawn
+    with a CUDA RNG op, so torch.manual_seed governs it and a captured CUDA graph gets fresh words on every replay."""
+    return torch.randint(0, 2 ** 31 - 1, (2,), dtype=torch.int32, device=device)
 
 
 def prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads: int, ws: Sequence[int], scale: float,
-                                     impl: int = IMPL_AUTO) -> torch.Tensor:
-    """qkv [B,P,N,3C] = [q | k | v] of one fused projection; kvp [B,I,2C] = [kp | vp] or None."""
+                                     impl: int = IMPL_AUTO, p_drop: float = 0.0, seed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv [B,P,N,3C] = [q | k | v] of one fused projection; kvp [B,I,2C] = [kp | vp] or None.
+    p_drop > 0: attention dropout after the softmax (window_attention.py:57) with the mask derived from `seed`
+    (int32 [2] on the device, default: new_dropout_seed); runs on the fp32-math kernels."""
     _require_cuda(qkv, kvp, th, tw, td, tok, ids)
     if qkv.shape[-1] % (3 * heads) != 0:
         raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
-    return _WindowAttentionPacked.apply(qkv, kvp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl)
+    if p_drop > 0 and seed is None:
+        seed = new_dropout_seed(qkv.device)
+    return _WindowAttentionPacked.apply(qkv, kvp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl, float(p_drop), seed)
 
 
 # ------------------------------------------------------------------------------------------------

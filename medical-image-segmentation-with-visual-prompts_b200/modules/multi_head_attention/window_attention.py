@@ -52,8 +52,11 @@ class WindowAttention(nn.Module):
         if pos_bias is None or not isinstance(pos_bias, BiasTables):
             raise NotImplementedError("WindowAttention on the fused kernels takes the compact BiasTables form of the "
                                       "position bias (RelativePE.tables), not a dense [1,1,h,N',N'] tensor")
-        if self.training and self.attn_drop.p > 0:
-            raise NotImplementedError("attn_drop > 0 in training mode is not implemented in the fused kernel yet")
+        # attention dropout (reference :57) happens INSIDE the fused kernel: the probabilities are never materialised.
+        # The mask comes from a counter-based hash of (seed words, sample, window, head, query, key); it cannot be the
+        # reference's torch Philox stream (that is indexed over a dense [B,P,h,N',N'] tensor which does not exist here).
+        p_drop = float(self.attn_drop.p) if self.training else 0.0
+        impl = PF.IMPL_AUTO if p_drop > 0 else self.impl      # dropout runs on the fp32-math kernels for now
         if q is k and k is v:
             # self-attention (the only way the block calls it): ONE fused [C -> 3C] projection GEMM; the kernels
             # read q|k|v as column blocks of its output (row stride 3C), prompt K/V likewise from [C -> 2C]
@@ -62,7 +65,7 @@ class WindowAttention(nn.Module):
             kvp = PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight, lowp=lp.get('kv')) \
                 if prompts is not None else None
             o = PF.prompted_window_attention_packed(qkv, kvp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
-                                                    self.num_heads, pos_bias.ws, self.scale, self.impl)
+                                                    self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop)
         else:
             qq = PF.multi_linear(q, None, self.to_q.weight)
             kk = PF.multi_linear(k, None, self.to_k.weight)
@@ -72,6 +75,6 @@ class WindowAttention(nn.Module):
                 kp = PF.multi_linear(prompts, None, self.to_k.weight)
                 vp = PF.multi_linear(prompts, None, self.to_v.weight)
             o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok,
-                                             mask, self.num_heads, pos_bias.ws, self.scale, self.impl)
+                                             mask, self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop)
         o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'), bias_grad=proj_bias_grad)
         return self.proj_drop(o)

@@ -209,10 +209,43 @@ def dense_bias(th, tw, td, tok) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # attention + block
 # --------------------------------------------------------------------------------------
-def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads):
+def dropout_keep_factor(seed_words, B, P, num_heads, N, NK, p_drop):
+    """The attention-dropout mask of the B200 kernels (csrc/attn.cuh: drop_row_state / drop_block_bits / drop_keep),
+    restated with numpy: float64 [B,P,h,N,NK] holding 0 for dropped and 1/keep_rate for kept entries.  The reference
+    applies nn.Dropout to the dense probabilities (window_attention.py:57); the kernels cannot reproduce torch's Philox
+    stream over a tensor they never materialise, so parity is: same distribution (Bernoulli, rate in steps of 1/256,
+    inverse-keep-rate scaling) and exact agreement with THIS mask for given seed words."""
+    M = np.uint64(0xFFFFFFFF)
+
+    def mix(x):
+        x = x & M
+        x ^= x >> np.uint64(16); x = (x * np.uint64(0x21f0aaad)) & M
+        x ^= x >> np.uint64(15); x = (x * np.uint64(0x735a2d97)) & M
+        x ^= x >> np.uint64(15)
+        return x
+
+    t = int(p_drop * 256.0 + 0.5)
+    t = min(t, 255)
+    if p_drop > 0 and t == 0:
+        t = 1
+    s0, s1 = (np.uint64(int(w) & 0xFFFFFFFF) for w in seed_words)
+    NH = (N + 1) // 2
+    bw = np.arange(B * P, dtype=np.uint64)[:, None, None, None]
+    hd = np.arange(num_heads, dtype=np.uint64)[None, :, None, None]
+    n = np.arange(N, dtype=np.uint64)[None, None, :, None]
+    j = np.arange(NK, dtype=np.uint64)[None, None, None, :]
+    rs = mix(s0 + (((bw * np.uint64(num_heads) + hd) * np.uint64(NH) + (n >> np.uint64(1))) * np.uint64(0x85EBCA77) & M)) ^ s1
+    bits = mix(rs ^ (((j >> np.uint64(1)) * np.uint64(0x9E3779B1)) & M))
+    byte = (bits >> (np.uint64(8) * ((n & np.uint64(1)) * np.uint64(2) + (j & np.uint64(1))))) & np.uint64(0xFF)
+    keep = byte >= np.uint64(t)
+    return torch.from_numpy(keep.astype(np.float64) * (256.0 / (256 - t))).reshape(B, P, num_heads, N, NK)
+
+
+def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads, drop=None):
     """q,k,v [B,P,N,C]; kp,vp [B,I,C] or None; bias [h,N,N+I]; ids int [P,N] or None.
-    window_attention.py:45-59: logits = (q.k^T*scale + bias) * mask, softmax over keys, @ v.
-    Prompt columns are never masked (swin_block.py:187-196)."""
+    window_attention.py:45-59: logits = (q.k^T*scale + bias) * mask, softmax over keys, [dropout,] @ v.
+    Prompt columns are never masked (swin_block.py:187-196).  drop: optional [B,P,h,N,N+I] keep factors
+    (0 or 1/keep_rate) applied to the probabilities (window_attention.py:57)."""
     B, P, N, C = q.shape
     dh = C // num_heads
 
@@ -235,6 +268,8 @@ def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads):
             m = torch.cat([m, m.new_ones(P, N, kp.shape[1])], dim=2)
         s = s * m[None, :, None]
     a = torch.softmax(s, dim=-1)
+    if drop is not None:
+        a = a * drop.to(a.dtype)
     o = torch.matmul(a, vh)                                                    # [B,P,h,N,dh]
     return o.permute(0, 1, 3, 2, 4).reshape(B, P, N, C)
 

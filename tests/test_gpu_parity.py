@@ -447,3 +447,75 @@ def test_pair_token_pipeline_equals_block_by_block(down):
             assert torch.equal(res[0][0], other[0])
             for a, b in zip(res[0][1:], other[1:]):
                 assert rel_linf(a, b) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+# attention dropout (window_attention.py:57) inside the fused kernels
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", [(2, 3, (4, 4, 2), 12, 4, 8, True), (1, 2, (8, 8, 4), 48, 4, 64, True), (2, 2, (3, 5, 2), 16, 2, 5, False),
+                                  (1, 2, (3, 3, 3), 12, 2, 3, True)])
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, RTOL_F32), (torch.bfloat16, RTOL_BF16)])
+def test_attention_dropout_matches_oracle_with_same_mask(case, dtype, rtol):
+    """With given seed words the forward, dQ and dK/dV kernels must all apply exactly the mask the oracle restates."""
+    B, P, ws, C, heads, I, masked = case
+    p_drop = 0.25
+    ten, ids, go = _attn_inputs(B, P, ws, C, heads, I, masked, seed=21)
+    N = ws[0] * ws[1] * ws[2]
+    scale = (C // heads) ** -0.5
+    seed = torch.tensor([123456789, 987654321], dtype=torch.int32)
+    drop = R.dropout_keep_factor(seed.tolist(), B, P, heads, N, N + I, p_drop)
+    rate = (drop == 0).double().mean().item()
+    assert abs(rate - 0.25) < 0.02
+    ten_r = [None if t is None else (t.to(dtype).double() if i < 5 else t.float().double()) for i, t in enumerate(ten)]
+    leaves = [t.clone().requires_grad_(True) if t is not None else None for t in ten_r]
+    q, k, v, kp, vp, th, tw, td, tok = leaves
+    ref = R.prompted_window_attention(q, k, v, kp, vp, R.dense_bias(th, tw, td, tok), None if ids is None else ids.numpy(), scale,
+                                      heads, drop=drop)
+    (ref * go.to(dtype).double()).sum().backward()
+    dev = [None if t is None else (t.to(DEV, dtype) if i < 5 else t.to(DEV, torch.float32)).requires_grad_(True)
+           for i, t in enumerate(ten)]
+    ids_d = None if ids is None else ids.to(DEV)
+    out = PF.prompted_window_attention(*dev, ids_d, heads, ws, scale, PF.IMPL_AUTO, p_drop=p_drop, seed=seed.to(DEV))
+    assert rel_linf(out, ref) < rtol
+    out.backward(go.to(DEV, dtype))
+    for n, t, l in zip(["q", "k", "v", "kp", "vp", "th", "tw", "td", "tok"], dev, leaves):
+        if t is not None:
+            assert rel_linf(t.grad, l.grad) < rtol, n
+    # no dropout requested -> identical to the plain call; a different seed -> a different mask
+    plain = PF.prompted_window_attention(*[t.detach() if t is not None else None for t in dev], ids_d, heads, ws, scale)
+    assert rel_linf(out, plain) > 1e-3
+    other = PF.prompted_window_attention(*[t.detach() if t is not None else None for t in dev], ids_d, heads, ws, scale,
+                                         PF.IMPL_AUTO, p_drop=p_drop, seed=(seed + 1).to(DEV))
+    assert rel_linf(out, other) > 1e-3
+
+
+def test_block_trains_with_the_reference_example_dropout():
+    """configurations/example_configs.yml:18-19 sets attn_drop = proj_drop = 0.1: the block must train with it (it used to
+    raise), stay deterministic under torch.manual_seed, be unbiased in expectation, and ignore dropout in eval mode."""
+    torch.manual_seed(0)
+    blk = pwa_b200.SwinTransformerBlock(hidden_channels=48, window_size=(8, 8, 4), pos_bias_embed_dim=64, num_heads=4,
+                                        max_prompts=1, tokens_per_prompt=64, shift_size=(4, 4, 2), attn_drop=0.1,
+                                        proj_drop=0.1).to(DEV)
+    x = torch.randn(2, 48, 16, 16, 8, device=DEV)
+    p = 0.2 * torch.randn(2, 64, 48, device=DEV)
+    blk.eval()
+    y_eval = blk(x, p)
+    assert torch.equal(y_eval, blk(x, p))
+    blk.train()
+    torch.manual_seed(5)
+    y1 = blk(x, p)
+    torch.manual_seed(5)
+    y2 = blk(x, p)
+    assert torch.equal(y1, y2)                                   # same generator state -> same masks
+    y3 = blk(x, p)
+    assert not torch.equal(y1, y3)
+    acc = torch.zeros_like(y_eval)
+    n_rep = 64
+    for _ in range(n_rep):
+        acc += blk(x, p)
+    assert rel_linf(acc / n_rep, y_eval) < 0.08                   # inverted dropout is unbiased (first order)
+    xg = x.clone().requires_grad_(True)
+    pg = p.clone().requires_grad_(True)
+    blk(xg, pg).square().sum().backward()
+    assert torch.isfinite(xg.grad).all() and torch.isfinite(pg.grad).all()
+    assert all(prm.grad is not None and torch.isfinite(prm.grad).all() for prm in blk.parameters())

@@ -111,7 +111,7 @@ typedef struct pwa_attn_shape {
   float scale;                 /* head_dim ** -0.5  (window_attention.py:25)       */
   float p_drop;                /* attention dropout probability (0 in eval), applied in steps of 1/256 after the
                                   softmax (window_attention.py:57); the forward and backward calls of one step must
-                                  see the same seed words.  Runs on the fp32-math kernels (impl 0 / 1).            */
+                                  see the same seed words (all kernels: tcgen05 and fp32-math).                    */
   uint64_t seed, offset;       /* host seed words (e.g. torch's generator seed / offset)                          */
   int32_t ld_qkv;              /* row stride (elements) of q,k,v and dq,dk,dv; 0 = C.  3*C when q|k|v are the
                                   column blocks of ONE fused projection output [B][P][N][3C]            */

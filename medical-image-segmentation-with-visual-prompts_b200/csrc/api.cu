@@ -78,8 +78,7 @@ extern "C" int pwa_attn_fwd(const void* q, const void* k, const void* v, const v
     p.delta = (float*)tl;
     g_fwd_timeline = tl;
   }
-  // (attention dropout currently runs on the fp32-math kernels only)
-  const bool tc_ok = attn_tc_supported(p, dtype) && p.drop_thresh == 0;
+  const bool tc_ok = attn_tc_supported(p, dtype);
   if (impl == 2 && !tc_ok) {
     set_error("pwa_attn_fwd: tcgen05 kernel does not support this shape/dtype");
     return PWA_ERR_UNSUPPORTED;
@@ -115,7 +114,7 @@ extern "C" int pwa_attn_bwd(const void* q, const void* k, const void* v, const v
     PWA_CUDA_OK(cudaMemsetAsync(dkp, 0, (size_t)p.B * p.I * p.C * 4, st));
     PWA_CUDA_OK(cudaMemsetAsync(dvp, 0, (size_t)p.B * p.I * p.C * 4, st));
   }
-  const bool tc_ok = attn_tc_bwd_supported(p, dtype) && p.drop_thresh == 0;
+  const bool tc_ok = attn_tc_bwd_supported(p, dtype);
   if (impl == 2 && !tc_ok) {
     set_error("pwa_attn_bwd: tcgen05 kernel does not support this shape/dtype");
     return PWA_ERR_UNSUPPORTED;

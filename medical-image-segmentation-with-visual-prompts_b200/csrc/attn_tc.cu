@@ -125,7 +125,11 @@ __device__ __forceinline__ void store_chunks(uint8_t* base, uint32_t chunk_strid
   }
 }
 
-template <int DH, bool MASKED>
+// DROP: attention dropout (window_attention.py:57).  The keep mask (csrc/attn.cuh: 32 hash bits per 2x2 block of
+// (query pair, key pair)) is applied to the PACKED bf16 probabilities with one AND per pair, after the shift mask;
+// the softmax denominator, which the ones column of V can no longer deliver, is then summed in registers from the
+// same bf16 values the MMA consumes, and the inverse keep rate is applied once in the epilogue.
+template <int DH, bool MASKED, bool DROP>
 __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) attn_fwd_tc_kernel(AttnParams p) {
   constexpr int DHP = Cfg<DH>::DHP, NDC = Cfg<DH>::NDC, KS = Cfg<DH>::KS;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -147,6 +151,9 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   const int head = blockIdx.x % p.heads;
   const float inv_scale = 1.f / p.scale;
   const float c2 = p.scale * 1.4426950408889634f;          // logits -> log2 domain
+  const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
+  const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
+  const uint32_t thresh4 = p.drop_thresh * 0x01010101u;
   const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
 
   // ---- once per CTA: window-independent halves of Q' and K', per-row upper bound of the bias ----
@@ -339,6 +346,9 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         }
         mb = mx * c2;
       }
+      const uint32_t rstate = DROP ? drop_row_state(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN / 2, (uint32_t)rown) : 0u;
+      const uint32_t rsh = (rown & 1) * 16;                      // this row's two bytes of a block's hash bits
+      float lsum = 0.f;
       const float e0 = fast_exp2(-mb);                           // weight of every masked (zeroed) logit
       const uint32_t e0pair = pack_bf16(e0, e0);
       const uint32_t* selrow = sel_s + id_slot(rid) * (kN / 4);
@@ -382,6 +392,15 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
               }
             }
           }
+          if (DROP) {
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+              lsum += __uint_as_float(pk[g] << 16) + __uint_as_float(pk[g] & 0xffff0000u);
+              const uint32_t bits = drop_block_bits(rstate, (uint32_t)(kb * 128 + c * 32 + 2 * g)) >> rsh;
+              // bytes 0 / 1 = keys 2g / 2g+1: per-byte (>= thresh) -> 0xff, spread to the two bf16 halves
+              pk[g] &= __byte_perm(__vcmpgeu4(bits, thresh4), 0u, 0x1100);
+            }
+          }
           tmem_st16(trow + c * 16, pk);
         }
         tmem_wait_st();
@@ -419,8 +438,8 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       }
 
       // ---- epilogue: normalise, write bf16 output row slice and log-sum-exp ----
-      const float l_run = o_run[DH];
-      const float inv = 1.f / l_run;
+      const float l_run = DROP ? lsum : o_run[DH];
+      const float inv = (DROP ? p.inv_keep : 1.f) / l_run;
       __nv_bfloat16* og = (__nv_bfloat16*)p.out + ((size_t)bw * kN + rown) * p.C + head * DH;
       if constexpr (DH % 4 == 0) {
 #pragma unroll
@@ -455,7 +474,8 @@ int launch_tc(const AttnParams& p, cudaStream_t st) {
   const int need = p.B * p.P * p.heads;
   if (grid > need) grid = need;
   if (grid < p.heads) grid = p.heads;
-  auto kern = p.ids ? attn_fwd_tc_kernel<DH, true> : attn_fwd_tc_kernel<DH, false>;
+  auto kern = p.drop_thresh ? (p.ids ? attn_fwd_tc_kernel<DH, true, true> : attn_fwd_tc_kernel<DH, false, true>)
+                            : (p.ids ? attn_fwd_tc_kernel<DH, true, false> : attn_fwd_tc_kernel<DH, false, false>);
   PWA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kRows, smem, st>>>(p);
   PWA_CUDA_OK(cudaGetLastError());

@@ -71,7 +71,7 @@ struct BwdSmem {
   // shared by all windows
   uint32_t qaug, kaug, g, gth, gtw, gtd, gtok;
   // per operand buffer (offsets relative to the buffer base)
-  uint32_t q, k, v, dO, lse2, delta, wp, sel, ids, opnd_bytes;
+  uint32_t q, k, v, dO, lse2, delta, wp, rs, sel, ids, opnd_bytes;
   uint32_t opnd0;        // base of operand buffer 0; buffer b at opnd0 + b * opnd_bytes
   int opb, gsb;          // number of operand / g^T buffers
   uint32_t total;
@@ -88,6 +88,7 @@ __host__ __device__ inline BwdSmem bwd_layout(int KS, int DHP, int NKT, int wh, 
   s.lse2 = o; o += kN * 4;
   s.delta = o; o += kN * 4;
   s.wp = o; o += kN * 2;                          // bf16 exp(-lse) per query (value of a masked P entry)
+  s.rs = o; o += (kN / 2) * 4;                    // dropout hash state per query pair (csrc/attn.cuh)
   s.sel = o; o += masked ? kIds * (kN / 4) * 4 : 0;   // PRMT selectors [id slot][4 tokens], as in attn_tc.cu
   s.ids = o; o += kN;
   s.opnd_bytes = (o + 127) & ~127u;
@@ -178,10 +179,13 @@ enum {
   kNumBars = 17
 };
 
-template <int DH, bool MASKED>
+// DROP: attention dropout (window_attention.py:57) with the mask of csrc/attn.cuh.  P^T feeds dV dropped (one AND on
+// the packed pairs, after the shift mask; the inverse keep rate is applied when dV is drained), dP^T is masked and
+// scaled before delta is subtracted (so delta cannot ride in the dP^T MMA: FOLD is off).
+template <int DH, bool MASKED, bool DROP>
 __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p) {
   constexpr int DHP = BCfg<DH>::DHP, KS = BCfg<DH>::KS, DKC = BCfg<DH>::DKC, NBUF = BCfg<DH>::NBUF;
-  constexpr bool FOLD = BCfg<DH>::FOLD;
+  constexpr bool FOLD = BCfg<DH>::FOLD && !DROP;
   // TMEM column map: NBUF x [S^T 64 | dP^T 64], then the accumulators
   constexpr uint32_t cACC = NBUF * 128, cDV = cACC, cDK = cDV + DHP, cDQ = cDK + DKC, cAUG = cDQ + 2 * DKC;
   static_assert(cAUG + 48 <= 512, "TMEM column budget");
@@ -205,6 +209,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   const int head = blockIdx.x % p.heads;
   const float inv_scale = 1.f / p.scale;
   const float c2 = p.scale * 1.4426950408889634f;
+  const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
+  const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
+  const uint32_t thresh4 = p.drop_thresh * 0x01010101u;
+  const float keep_scale = DROP ? p.inv_keep : 1.f;
   const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
 
   // ---- once per CTA: zero everything the MMAs may touch beyond the staged rows, window-independent operands ----
@@ -306,6 +314,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       const float* lse2_s = reinterpret_cast<const float*>(opnd + L.lse2);
       const float* delta_s = reinterpret_cast<const float*>(opnd + L.delta);
       const __nv_bfloat16* wp_s = reinterpret_cast<const __nv_bfloat16*>(opnd + L.wp);
+      const uint32_t* rs_s = reinterpret_cast<const uint32_t*>(opnd + L.rs);
       const uint32_t* sel_s = reinterpret_cast<const uint32_t*>(opnd + L.sel);
       const uint8_t* ids_s = opnd + L.ids;
       STAMP(1);
@@ -341,6 +350,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             tmem_ld16(trow + cP + wg * 32 + h * 16, dp);
             tmem_wait_ld();
             uint32_t pk[8], gk[8];
+            uint32_t dmask[DROP ? 8 : 1];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const float4 l4 = *reinterpret_cast<const float4*>(lse2_s + r0 + h * 16 + q4 * 4);
@@ -351,14 +361,28 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
                 dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
               }
               float pv[4], gv[4];
+              uint32_t keep[2] = {0xffffffffu, 0xffffffffu};       // per row pair: byte 0 / byte 2 = first / second row
+              if (DROP) {
+                const int rp = (r0 + h * 16 + q4 * 4) >> 1;
+                const uint32_t jb = 8u * ((uint32_t)lane_row & 1u);
+                const uint32_t key = (uint32_t)(kb * 128 + lane_row);
+                keep[0] = __vcmpgeu4(drop_block_bits(rs_s[rp], key) >> jb, thresh4);
+                keep[1] = __vcmpgeu4(drop_block_bits(rs_s[rp + 1], key) >> jb, thresh4);
+              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int r = q4 * 4 + e;
                 pv[e] = fast_exp2(fmaf(__uint_as_float(s[r]), c2, -lv[e]));
-                gv[e] = pv[e] * (FOLD ? __uint_as_float(dp[r]) : __uint_as_float(dp[r]) - dv[e]);
+                float dpe = __uint_as_float(dp[r]);
+                if (DROP) dpe = (keep[e >> 1] & ((e & 1) ? 0xff0000u : 0xffu)) ? dpe * keep_scale : 0.f;
+                gv[e] = pv[e] * (FOLD ? dpe : dpe - dv[e]);
               }
               pk[q4 * 2] = pack_bf16(pv[0], pv[1]);
               pk[q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
+              if (DROP) {                                          // (applied below, after the shift mask)
+                dmask[q4 * 2] = __byte_perm(keep[0], 0u, 0x2200);
+                dmask[q4 * 2 + 1] = __byte_perm(keep[1], 0u, 0x2200);
+              }
               gk[q4 * 2] = pack_bf16(gv[0], gv[1]);
               gk[q4 * 2 + 1] = pack_bf16(gv[2], gv[3]);
             }
@@ -375,6 +399,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
                 gk[w * 2] = prmt(gk[w * 2], 0u, sw[w]);
                 gk[w * 2 + 1] = prmt(gk[w * 2 + 1], 0u, sw[w] >> 16);
               }
+            }
+            if (DROP) {
+#pragma unroll
+              for (int w = 0; w < 8; ++w) pk[w] &= dmask[w];       // dropped P^T entries do not reach dV
             }
             tmem_st8(trow + cS + wg * 32 + h * 8, pk);             // packed over this warpgroup's own consumed columns
             tmem_st8(trow + cP + wg * 32 + h * 8, gk);
@@ -413,11 +441,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             mbar_arrive(&bar[bAccFree]);
             if (key_ok) {
               if (kb < 2) {
-                store_row_b<DH>((__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH, dv, 1.f);
+                store_row_b<DH>((__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH, dv, keep_scale);
               } else {
                 float* gp = p.dvp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
 #pragma unroll
-                for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dv[d]);
+                for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dv[d] * keep_scale);
               }
             }
           } else {
@@ -623,10 +651,14 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       float* lse2_s = reinterpret_cast<float*>(opnd + L.lse2);
       float* delta_s = reinterpret_cast<float*>(opnd + L.delta);
       __nv_bfloat16* wp_s = reinterpret_cast<__nv_bfloat16*>(opnd + L.wp);
+      uint32_t* rs_s = reinterpret_cast<uint32_t*>(opnd + L.rs);
       uint32_t* sel_s = reinterpret_cast<uint32_t*>(opnd + L.sel);
       uint8_t* ids_s = opnd + L.ids;
       if (it >= OPB) mbar_wait(&bar[bOpFree + ob], ((it / OPB) - 1) & 1);
       STAMP(1);
+      if (DROP)
+        for (int m = pt; m < kN / 2; m += kProd)
+          rs_s[m] = drop_row_state(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN / 2, (uint32_t)(2 * m));
       for (int n = pt; n < kN; n += kProd) {                       // query rows: Q', dO' (+ delta, lse)
         const size_t goff = ((size_t)bw * kN + n) * p.C + head * DH;
         __nv_bfloat16 row[DH], drow[DH], orow[DH];
@@ -703,7 +735,8 @@ int launch_bwd_tc(const AttnParams& p, cudaStream_t st) {
   if (grid < p.heads) grid = p.heads;
   const int need = p.B * p.P * p.heads;
   if (grid > need) grid = need;
-  auto kern = p.ids ? attn_bwd_tc_kernel<DH, true> : attn_bwd_tc_kernel<DH, false>;
+  auto kern = p.drop_thresh ? (p.ids ? attn_bwd_tc_kernel<DH, true, true> : attn_bwd_tc_kernel<DH, false, true>)
+                            : (p.ids ? attn_bwd_tc_kernel<DH, true, false> : attn_bwd_tc_kernel<DH, false, false>);
   PWA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kThreadsB, smem, st>>>(p);
   PWA_CUDA_OK(cudaGetLastError());

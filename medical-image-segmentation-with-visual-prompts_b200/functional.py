@@ -501,7 +501,7 @@ def prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads: int,
                                      impl: int = IMPL_AUTO, p_drop: float = 0.0, seed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """qkv [B,P,N,3C] = [q | k | v] of one fused projection; kvp [B,I,2C] = [kp | vp] or None.
     p_drop > 0: attention dropout after the softmax (window_attention.py:57) with the mask derived from `seed`
-    (int32 [2] on the device, default: new_dropout_seed); runs on the fp32-math kernels."""
+    (int32 [2] on the device, default: new_dropout_seed)."""
     _require_cuda(qkv, kvp, th, tw, td, tok, ids)
     if qkv.shape[-1] % (3 * heads) != 0:
         raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')

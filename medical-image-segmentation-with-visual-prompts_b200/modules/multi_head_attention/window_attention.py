@@ -56,7 +56,7 @@ class WindowAttention(nn.Module):
         # The mask comes from a counter-based hash of (seed words, sample, window, head, query, key); it cannot be the
         # reference's torch Philox stream (that is indexed over a dense [B,P,h,N',N'] tensor which does not exist here).
         p_drop = float(self.attn_drop.p) if self.training else 0.0
-        impl = PF.IMPL_AUTO if p_drop > 0 else self.impl      # dropout runs on the fp32-math kernels for now
+        impl = self.impl
         if q is k and k is v:
             # self-attention (the only way the block calls it): ONE fused [C -> 3C] projection GEMM; the kernels
             # read q|k|v as column blocks of its output (row stride 3C), prompt K/V likewise from [C -> 2C]

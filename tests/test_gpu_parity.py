@@ -519,3 +519,34 @@ def test_block_trains_with_the_reference_example_dropout():
     blk(xg, pg).square().sum().backward()
     assert torch.isfinite(xg.grad).all() and torch.isfinite(pg.grad).all()
     assert all(prm.grad is not None and torch.isfinite(prm.grad).all() for prm in blk.parameters())
+
+
+@pytest.mark.parametrize("case", [(1, 2, (8, 8, 4), 48, 4, 64, True), (2, 3, (8, 8, 4), 48, 4, 64, False), (1, 1, (8, 8, 4), 96, 4, 64, True),
+                                  (1, 1, (8, 8, 4), 192, 4, 64, True), (1, 2, (8, 8, 4), 48, 4, 0, True)])
+def test_attention_dropout_tcgen05_matches_oracle_with_same_mask(case):
+    """The tcgen05 forward / backward kernels apply the same hash mask as the fp32-math kernels and the oracle."""
+    B, P, ws, C, heads, I, masked = case
+    p_drop, dtype = 0.1, torch.bfloat16
+    ten, ids, go = _attn_inputs(B, P, ws, C, heads, I, masked, seed=23)
+    N = ws[0] * ws[1] * ws[2]
+    scale = (C // heads) ** -0.5
+    seed = torch.tensor([31337, 271828], dtype=torch.int32)
+    drop = R.dropout_keep_factor(seed.tolist(), B, P, heads, N, N + I, p_drop)
+    ten_r = [None if t is None else (t.to(dtype).double() if i < 5 else t.float().double()) for i, t in enumerate(ten)]
+    leaves = [t.clone().requires_grad_(True) if t is not None else None for t in ten_r]
+    q, k, v, kp, vp, th, tw, td, tok = leaves
+    ref = R.prompted_window_attention(q, k, v, kp, vp, R.dense_bias(th, tw, td, tok), None if ids is None else ids.numpy(), scale,
+                                      heads, drop=drop)
+    (ref * go.to(dtype).double()).sum().backward()
+    dev = [None if t is None else (t.to(DEV, dtype) if i < 5 else t.to(DEV, torch.float32)).requires_grad_(True)
+           for i, t in enumerate(ten)]
+    ids_d = None if ids is None else ids.to(DEV)
+    out = PF.prompted_window_attention(*dev, ids_d, heads, ws, scale, PF.IMPL_TC, p_drop=p_drop, seed=seed.to(DEV))
+    assert rel_linf(out, ref) < RTOL_BF16
+    out32 = PF.prompted_window_attention(*[t.detach() if t is not None else None for t in dev], ids_d, heads, ws, scale,
+                                         PF.IMPL_F32, p_drop=p_drop, seed=seed.to(DEV))
+    assert rel_linf(out, out32) < RTOL_BF16
+    out.backward(go.to(DEV, dtype))
+    for n, t, l in zip(["q", "k", "v", "kp", "vp", "th", "tw", "td", "tok"], dev, leaves):
+        if t is not None:
+            assert rel_linf(t.grad, l.grad) < RTOL_BF16, n

@@ -217,10 +217,15 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   const int n_pairs = p.B * p.P;
   const int stride = gridDim.x / p.heads;
 
+  // clock64 timeline of thread 0 / CTA 0 (tools/timeline_fwd.py): compiled in only with -DPWA_TIMELINE_BUILD
+#ifdef PWA_TIMELINE_BUILD
   long long* tl = reinterpret_cast<long long*>(p.delta);
   int tli = 0;
   const bool rec = p.debug && p.delta != nullptr && blockIdx.x == 0 && tid == 0;
 #define STAMP(tag) do { if (rec && tli < 2000) { tl[2 * tli] = clock64(); tl[2 * tli + 1] = (tag); ++tli; } } while (0)
+#else
+#define STAMP(tag) do { } while (0)
+#endif
 
   // S = Q'.K'^T for (query tile mt, key block kb); single thread
   auto issue_s = [&](int mt, int kb) {
@@ -245,6 +250,55 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
     __nv_bfloat16 extra[4];
     float qn2[2];
     float kmax2 = 0.f;
+    constexpr int kKR = 3;                                 // key rows per thread: N + I <= 3 * 128
+    constexpr bool kBatch = DH <= 24;                      // all global loads of the window in flight before the first use
+    if constexpr (kBatch) {
+      __nv_bfloat16 qrow[2][DH], krow[kKR][DH], vrow[kKR][DH];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + t * kRows + tid) * p.ldq + head * DH, qrow[t]);
+#pragma unroll
+      for (int u = 0; u < kKR; ++u) {
+        const int j = u * kRows + tid;
+        if (j < NKT) {
+          const bool content = j < kN;
+          const size_t off = content ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
+          load_row<DH>((const __nv_bfloat16*)(content ? p.k : p.kp) + off, krow[u]);
+          load_row<DH>((const __nv_bfloat16*)(content ? p.v : p.vp) + off, vrow[u]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int n = t * kRows + tid;
+        qn2[t] = sumsq<DH>(qrow[t]);
+        const int id_ = n % p.wd;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
+        store_chunks<DH, KS>(Qs, kN * 16, n, qrow[t], extra, p.wd);
+      }
+#pragma unroll
+      for (int u = 0; u < kKR; ++u) {
+        const int j = u * kRows + tid;
+        if (j < NKT) {
+          const bool content = j < kN;
+          kmax2 = fmaxf(kmax2, sumsq<DH>(krow[u]));
+          const int jd = j % p.wd;
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            extra[x] = (content && x < p.wd) ? __float2bfloat16(p.td[(head * p.wd + x) * p.wd + jd] * inv_scale) : zero;
+          store_chunks<DH, KS>(Ks, NKT * 16, j, krow[u], extra, p.wd);
+#pragma unroll
+          for (int dc = 0; dc < NDC; ++dc) {
+            __align__(16) __nv_bfloat16 tmp[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              tmp[e] = (dc * 8 + e < DH) ? vrow[u][dc * 8 + e < DH ? dc * 8 + e : 0] : (dc * 8 + e == DH ? one : zero);
+            *reinterpret_cast<uint4*>(Vs + (j >> 3) * (NDC * 128) + dc * 128 + (j & 7) * 16) =
+                *reinterpret_cast<const uint4*>(tmp);
+          }
+        }
+      }
+    } else {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int n = t * kRows + tid;
@@ -277,14 +331,17 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
             *reinterpret_cast<const uint4*>(tmp);
       }
     }
-    if (MASKED)
+    }
+    if (MASKED) {
       for (int i = tid; i < kN / 4; i += kRows)
         reinterpret_cast<uint32_t*>(ids_s)[i] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[i];
+    }
     kmax2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(kmax2)));   // non-negative floats order as uints
     if (lane == 0) kmax_s[warp] = __float_as_uint(kmax2);
     fence_proxy_async_smem();
     __syncthreads();
     if (MASKED) {
+      // (a table precomputed per geometry and loaded from L2 was measured slower than rebuilding it here)
       // PRMT selectors: word w of row-id slot s covers keys 4w..4w+3 = packed pairs 2w (low half) and 2w+1 (high half);
       // a kept bf16 takes its own bytes (nibbles 1,0 / 3,2), a masked one the bytes of the (e0,e0) operand (5,4 / 7,6)
       for (int i = tid; i < kIds * (kN / 4); i += kRows) {

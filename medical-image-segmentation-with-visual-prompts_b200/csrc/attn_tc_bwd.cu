@@ -281,6 +281,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   const int stride = gridDim.x / p.heads;
   const int bw0 = blockIdx.x / p.heads;
 
+  // clock64 timelines of CTA 0 (tools/timeline.py): compiled in only with -DPWA_TIMELINE_BUILD
+#ifdef PWA_TIMELINE_BUILD
   long long* tl = reinterpret_cast<long long*>(p.delta);
   int tli = 0;
   const bool rec = p.debug && blockIdx.x == 0 &&
@@ -289,6 +291,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   const int tlb = tid == 0 ? 0 : (tid == kIssue0 * 32 ? 2048 : (tid == (kIssue0 + 1) * 32 ? 4096 : (tid == 256 ? 8192 :
                   (tid == (kIssue0 + 4) * 32 ? 10240 : 6144))));
 #define STAMP(tag) do { if (rec && tli < 1000) { tl[tlb + 2 * tli] = clock64(); tl[tlb + 2 * tli + 1] = (tag); ++tli; } } while (0)
+#else
+#define STAMP(tag) do { } while (0)
+#endif
 
   if (warp < kIssue0) {
     // =============================================================================================

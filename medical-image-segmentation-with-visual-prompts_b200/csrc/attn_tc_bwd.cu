@@ -1,6 +1,6 @@
 // (c) backward of the fused prompted window attention on tcgen05 tensor cores + TMEM, bf16 I/O.
 //
-// One persistent CTA per SM (512 threads, all 512 TMEM columns) = one fixed head, walking over (sample, window)
+// One persistent CTA per SM (768 threads, all 512 TMEM columns) = one fixed head, walking over (sample, window)
 // pairs.  Everything is computed in the TRANSPOSED orientation: the 128 TMEM lanes are KEYS (one key block:
 // content 0-127, content 128-255, prompt tokens) and the TMEM columns are query rows, one UNIT = 64 rows:
 //     S^T [128k x 64r] = K'.Q'^T      dP^T [128k x 64r] = V'.dO'^T        (SS MMAs, fp32 accum in TMEM)
@@ -20,11 +20,18 @@
 // issued by different warps overlap (csrc/ubench.cu).  A clock64 timeline of the previous, barrier-synchronous
 // version showed 500 clk of MUFU work per unit against 1700 clk of exposed MMA latency, so the CTA is
 // warp-specialised and every hand-off is an mbarrier:
-//     warps 0-7   compute (key = tid % 128, warpgroup = row half): TMEM ld -> exp/mul/pack -> TMEM st + g^T to smem
-//     warp  8     issues S^T / dP^T of unit g as soon as the chains of unit g - NBUF have consumed that buffer
-//     warps 9-11  issue the dV / dK' / dKaug chains of a unit when its packed operands are ready
-//     warp  12    issues dQ' per (key block, query tile)
-//     warps 13-15 stage the NEXT window's operands into the other half of a double buffer (global -> smem)
+//     warps 0-15  compute, two groups of 8 that ping-pong over the units (group 0: even units, group 1: odd units + all
+//                 accumulator drains; key = tid % 128, warpgroup = row half, two passes of 16 rows to stay within the
+//                 80-register budget of a 768-thread CTA): TMEM ld -> exp/mul/pack -> TMEM st + g^T to smem.  The
+//                 waits / TMEM round trips / proxy fences of one group hide behind the exponentials of the other.
+//     warp  16    issues S^T / dP^T of unit g as soon as the chains of unit g - NBUF have consumed that buffer
+//     warps 17-19 issue the dV / dK' / dKaug chains of a unit when its packed operands are ready
+//     warp  20    issues dQ' per (key block, query tile)
+//     warps 21-23 stage the NEXT window's operands into the other half of a double buffer (global -> smem)
+// Measured (tools/timeline.py, `make TIMELINE=1`): the kernel is now bound by the tensor pipe's per-instruction cost --
+// 228 small MMAs per window at ~50 clk each whatever their N (csrc/ubench.cu), plus the stalls of five in-order
+// streams with dependent accumulations -- not by the MUFU pipe; fewer, fatter MMAs (merged dK'/dKaug chains, 128-row
+// units) are the next step.
 // S^T / dP^T are NBUF-fold buffered in TMEM (3 x 128 columns at head_dim <= 12), so the compute warps run
 // back to back on the MUFU pipe while the tensor pipe works 1-2 units behind / ahead.
 // Semantics follow the reference autograd of window_attention.py:49-58 (mask multiplicative, pre-softmax:

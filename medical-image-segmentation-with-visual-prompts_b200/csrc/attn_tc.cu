@@ -251,7 +251,9 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
     float qn2[2];
     float kmax2 = 0.f;
     constexpr int kKR = 3;                                 // key rows per thread: N + I <= 3 * 128
-    constexpr bool kBatch = DH <= 24;                      // all global loads of the window in flight before the first use
+    // all global loads of the window in flight before the first use (the masked variant is at its 128-register cap:
+    // batching spills there and measured 8 % slower)
+    constexpr bool kBatch = DH <= 24 && !MASKED;
     if constexpr (kBatch) {
       __nv_bfloat16 qrow[2][DH], krow[kKR][DH], vrow[kKR][DH];
 #pragma unroll

@@ -14,8 +14,8 @@
 // partition:  TMA load -> smem [c][a'][D_box]  --transpose-->  smem token blocks  -> coalesced 16-byte stores
 // reverse  :  coalesced 16-byte loads (+ fused residual add) -> smem token blocks --transpose--> smem [c][a'][D_box]
 //             -> TMA store
-// Persistent CTAs; the partition kernel double-buffers the TMA loads behind an mbarrier (tile i+1 is in flight
-// while tile i is transposed and stored).  Pure byte movement: bit-exact by construction.
+// Persistent CTAs, 2-4 per SM; the partition kernel can keep up to 3 more TMA loads in flight behind an mbarrier
+// (PWA_TMA_STAGES; measured no faster than more resident CTAs).  Pure byte movement: bit-exact by construction.
 //
 // Shared-memory layouts are chosen so that both sides of the transposition are bank-conflict free:
 //   * D_box = padded line length rounded up to an ODD number of 16-byte chunks: lanes that differ in a' hit
@@ -36,8 +36,8 @@ namespace {
 // Measured on B200 (profiles/r1_tma_partition.md): one 43 KB box of 384 lines x 96(+16) bytes takes the SM's TMA unit
 // ~3.4 us (~17 clk per line) whatever the pipeline depth, the split into several boxes or the number of warps (256 ->
 // 1024 threads made it slower), i.e. the kernels are bound by the TMA line rate for short lines, not by the SM side.
-constexpr int kPartThreads = 256;    // partition: one CTA per SM (3 staged tiles)
-constexpr int kRevThreads = 256;     // reverse: two CTAs per SM
+constexpr int kPartThreads = 256;
+constexpr int kRevThreads = 256;
 constexpr int kMaxStages = 4;
 constexpr int kWW = 8;            // lanes are mapped as (a' = lane & 7, channel word = lane >> 3)
 
@@ -223,7 +223,7 @@ __device__ __forceinline__ Piece piece(const TmaPartParams& p, const Tile& t, ui
 }
 
 template <int EB>
-__global__ void __launch_bounds__(kPartThreads, 1) partition_tma_kernel(const __grid_constant__ CUtensorMap xmap,
+__global__ void __launch_bounds__(kPartThreads, 4) partition_tma_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                     uint32_t* __restrict__ tok, const TmaPartParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t full[kMaxStages];
@@ -286,7 +286,7 @@ template <int EB> __device__ __forceinline__ uint32_t addw(uint32_t a, uint32_t 
 }
 
 template <int EB, bool ADD>
-__global__ void __launch_bounds__(kRevThreads, 2) reverse_tma_kernel(const __grid_constant__ CUtensorMap xmap,
+__global__ void __launch_bounds__(kRevThreads, 4) reverse_tma_kernel(const __grid_constant__ CUtensorMap xmap,
                                                                   const uint32_t* __restrict__ tok,
                                                                   const uint32_t* __restrict__ tok2, const TmaPartParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -352,7 +352,10 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 
+// Measured (profiles/r1_tma_partition.md): two or more resident CTAs per SM beat one CTA with a 3-deep TMA pipeline
+// (24 vs 29 us), so a tile (one staged x box + the token blocks) is sized for >= 2 CTAs per SM when the shape allows.
 constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemTwoCtas = 110 * 1024;
 
 bool plan(TmaPartParams& p, int B, int C, const pwa_geom* g, const int32_t* lo, int eb) {
   if (g->ws[1] != kWW) return false;
@@ -377,6 +380,7 @@ bool plan(TmaPartParams& p, int B, int C, const pwa_geom* g, const int32_t* lo, 
   p.dbox = chunks * epv;
   if (p.dbox > 256) return false;
   // channel chunk: all channels if the tile fits (double-buffered, else single), otherwise halve
+  for (int pass = 0; pass < 2; ++pass)                             // pass 0: tiles that leave room for two CTAs per SM
   for (int ct = C; ct >= epv; ct /= 2) {
     if (C % ct != 0 || (ct * eb) % 16 != 0 || ct > 256) continue;
     p.CT = ct;
@@ -388,10 +392,10 @@ bool plan(TmaPartParams& p, int B, int C, const pwa_geom* g, const int32_t* lo, 
     p.box_bytes = ct * kWW * p.dbox * eb;
     p.src_bytes = (p.box_bytes + 127) & ~127;
     const size_t dst_bytes = (size_t)p.P3 * kWW * p.bp * 4, tab = (size_t)p.dbox * 4 + 16;
-    static const int max_stages = getenv("PWA_TMA_STAGES") ? atoi(getenv("PWA_TMA_STAGES")) : 3;
-    static const int want_split = getenv("PWA_TMA_SPLIT") ? atoi(getenv("PWA_TMA_SPLIT")) : 4;
+    static const int max_stages = getenv("PWA_TMA_STAGES") ? atoi(getenv("PWA_TMA_STAGES")) : 1;
+    static const int want_split = getenv("PWA_TMA_SPLIT") ? atoi(getenv("PWA_TMA_SPLIT")) : 1;
     for (int ns = max_stages < kMaxStages ? max_stages : kMaxStages; ns >= 1; --ns) {
-      if ((size_t)ns * p.src_bytes + dst_bytes + tab <= kSmemBudget) {
+      if ((size_t)ns * p.src_bytes + dst_bytes + tab <= (pass == 0 ? kSmemTwoCtas : kSmemBudget)) {
         p.nstage = ns;
         p.nsplit = 1;
         for (int k = want_split; k > 1; k /= 2)
@@ -453,7 +457,7 @@ int partition_tma_run(bool is_partition, const void* src, const void* src2, void
   if (!make_map(&map, xptr, p, eb, p.nsplit)) return PWA_ERR_UNSUPPORTED;
   const size_t smem = smem_bytes(p, p.nstage);
   int per_sm = (int)((227 * 1024) / (smem + 1024));
-  per_sm = per_sm < 1 ? 1 : (per_sm > (is_partition ? 1 : 2) ? (is_partition ? 1 : 2) : per_sm);
+  per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
   int grid = 148 * per_sm;
   if (grid > p.ntiles) grid = p.ntiles;
   bool ok;

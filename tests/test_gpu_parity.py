@@ -550,3 +550,49 @@ def test_attention_dropout_tcgen05_matches_oracle_with_same_mask(case):
     for n, t, l in zip(["q", "k", "v", "kp", "vp", "th", "tw", "td", "tok"], dev, leaves):
         if t is not None:
             assert rel_linf(t.grad, l.grad) < RTOL_BF16, n
+
+
+# --------------------------------------------------------------------------------------------------
+# BASELINE configs beyond cfg2: frozen backbone (cfg4) and 128^3 patches (cfg5)
+# --------------------------------------------------------------------------------------------------
+def test_frozen_backbone_prompt_only_gradients():
+    """cfg4 (downstream few-shot): only the prompt tokens (and prompt-bias parameters) require grad.  Their gradients
+    must equal those of a fully trainable run, and frozen parameters must not receive any."""
+    torch.manual_seed(3)
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=48, num_heads=4, pos_bias_embed_dim=64, max_prompts=1,
+                                          tokens_per_prompt=64, window_size=(8, 8, 4), down=True).to(DEV)
+    x = torch.randn(2, 48, 16, 16, 8, device=DEV)
+    prompts = [torch.nn.Parameter(0.2 * torch.randn(64, 48, device=DEV)) for _ in range(2)]
+
+    def run():
+        for prm in list(pair.parameters()) + prompts:
+            prm.grad = None
+        p = tuple(t.unsqueeze(0).expand(2, -1, -1) for t in prompts)
+        pair(x, p).square().sum().backward()
+        return [t.grad.clone() for t in prompts], [prm.grad for _, prm in pair.named_parameters_bias_prompt_tokens()]
+
+    g_full, gb_full = run()
+    trainable = {id(prm) for _, prm in pair.named_parameters_bias_prompt_tokens()}
+    for prm in pair.parameters():
+        prm.requires_grad_(id(prm) in trainable)
+    g_frozen, gb_frozen = run()
+    for a, b in zip(g_full + [g.clone() for g in gb_full], g_frozen + gb_frozen):
+        assert rel_linf(b, a) < 1e-5
+    assert all(prm.grad is None for prm in pair.parameters() if id(prm) not in trainable)
+
+
+def test_stage_shapes_of_128_cubed_patches():
+    """cfg5: 128^3 patches give 64^3 / 32^3 / 16x16x32 feature maps (P = 1024 / 128 / 32 windows).  The
+    bf16 stage must run forward + backward there and agree with the fp32-math path on a sample."""
+    torch.manual_seed(4)
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=48, num_heads=4, pos_bias_embed_dim=64, max_prompts=1,
+                                          tokens_per_prompt=64, window_size=(8, 8, 4), down=True, merge_last_dim=True).to(DEV)
+    x = torch.randn(1, 48, 64, 64, 64, device=DEV)
+    p = tuple(0.2 * torch.randn(1, 64, 48, device=DEV) for _ in range(2))
+    y32 = pair(x, p)
+    xb = x.bfloat16().requires_grad_(True)
+    y16 = pair(xb, tuple(t.bfloat16() for t in p))
+    assert tuple(y16.shape) == (1, 96, 32, 32, 32)
+    assert rel_linf(y16, y32) < 2 * RTOL_BF16                    # two blocks + merge in bf16 end to end
+    y16.float().square().mean().backward()
+    assert torch.isfinite(xb.grad.float()).all()

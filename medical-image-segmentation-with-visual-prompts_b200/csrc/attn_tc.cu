@@ -157,6 +157,26 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
 
   // ---- once per CTA: window-independent halves of Q' and K', per-row upper bound of the bias ----
+  // (the bias tables of this head go through shared memory first: the loops below read each entry many times, and
+  //  chains of dependent global loads made this setup ~20 % of the kernel at the small stages)
+  __shared__ float tab_s[16 * 16 + 4 * 4 + 128 + 4];            // th | tw (wh + ww <= 16) | td (wd <= 4) | tok (I <= 128) | max tok
+  float* th_s = tab_s;
+  float* tw_s = th_s + p.wh * p.wh;
+  float* td_s = tw_s + p.ww * p.ww;
+  float* tok_s = td_s + p.wd * p.wd;
+  for (int i = tid; i < p.wh * p.wh; i += kRows) th_s[i] = p.th[head * p.wh * p.wh + i];
+  for (int i = tid; i < p.ww * p.ww; i += kRows) tw_s[i] = p.tw[head * p.ww * p.ww + i];
+  for (int i = tid; i < p.wd * p.wd; i += kRows) td_s[i] = p.td[head * p.wd * p.wd + i];
+  for (int i = tid; i < p.I; i += kRows) tok_s[i] = p.tok[head * p.I + i];
+  __syncthreads();
+  if (warp == 0) {
+    float bt = -1e30f;
+    for (int j = lane; j < p.I; j += 32) bt = fmaxf(bt, tok_s[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bt = fmaxf(bt, __shfl_xor_sync(0xffffffffu, bt, o));
+    if (lane == 0) tok_s[p.I] = bt;
+  }
+  __syncthreads();
   for (int n = tid; n < kN; n += kRows) {
     const int id_ = n % p.wd, iw = (n / p.wd) % p.ww, ih = n / (p.wd * p.ww);
 #pragma unroll
@@ -169,11 +189,11 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       }
       *reinterpret_cast<uint4*>(Qa + c * (kN * 16) + n * 16) = *reinterpret_cast<const uint4*>(tmp);
     }
-    float bh = -1e30f, bw = -1e30f, bd = -1e30f, bt = -1e30f;
-    for (int j = 0; j < p.wh; ++j) bh = fmaxf(bh, p.th[(head * p.wh + ih) * p.wh + j]);
-    for (int j = 0; j < p.ww; ++j) bw = fmaxf(bw, p.tw[(head * p.ww + iw) * p.ww + j]);
-    for (int j = 0; j < p.wd; ++j) bd = fmaxf(bd, p.td[(head * p.wd + id_) * p.wd + j]);
-    for (int j = 0; j < p.I; ++j) bt = fmaxf(bt, p.tok[head * p.I + j]);
+    float bh = -1e30f, bw = -1e30f, bd = -1e30f;
+    const float bt = tok_s[p.I];
+    for (int j = 0; j < p.wh; ++j) bh = fmaxf(bh, th_s[ih * p.wh + j]);
+    for (int j = 0; j < p.ww; ++j) bw = fmaxf(bw, tw_s[iw * p.ww + j]);
+    for (int j = 0; j < p.wd; ++j) bd = fmaxf(bd, td_s[id_ * p.wd + j]);
     rowb_s[n] = (p.I > 0 ? fmaxf(bh + bw + bd, bt) : bh + bw + bd) * inv_scale;   // max_j bias[n][j] / scale
   }
   for (int j = tid; j < NKT; j += kRows) {
@@ -187,10 +207,10 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         const int col = c * 8 + e;
         float v = 0.f;
         if (content) {
-          if (col < p.wh) v = p.th[(head * p.wh + col) * p.wh + jh];
-          else if (col - p.wh < p.ww) v = p.tw[(head * p.ww + (col - p.wh)) * p.ww + jw];
+          if (col < p.wh) v = th_s[col * p.wh + jh];
+          else if (col - p.wh < p.ww) v = tw_s[(col - p.wh) * p.ww + jw];
         } else if (col < p.wh) {
-          v = p.tok[head * p.I + (j - kN)];
+          v = tok_s[j - kN];
         }
         tmp[e] = __float2bfloat16(v * inv_scale);
       }
@@ -287,7 +307,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
           const int jd = j % p.wd;
 #pragma unroll
           for (int x = 0; x < 4; ++x)
-            extra[x] = (content && x < p.wd) ? __float2bfloat16(p.td[(head * p.wd + x) * p.wd + jd] * inv_scale) : zero;
+            extra[x] = (content && x < p.wd) ? __float2bfloat16(td_s[x * p.wd + jd] * inv_scale) : zero;
           store_chunks<DH, KS>(Ks, NKT * 16, j, krow[u], extra, p.wd);
 #pragma unroll
           for (int dc = 0; dc < NDC; ++dc) {
@@ -321,7 +341,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       const int jd = j % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        extra[u] = (content && u < p.wd) ? __float2bfloat16(p.td[(head * p.wd + u) * p.wd + jd] * inv_scale) : zero;
+        extra[u] = (content && u < p.wd) ? __float2bfloat16(td_s[u * p.wd + jd] * inv_scale) : zero;
       store_chunks<DH, KS>(Ks, NKT * 16, j, row, extra, p.wd);
       load_row<DH>((const __nv_bfloat16*)(content ? p.v : p.vp) + off, row);
 #pragma unroll

@@ -201,6 +201,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   __shared__ __align__(8) uint64_t bar[kNumBars];
   __shared__ uint32_t tmem_base_s;
 
+#ifdef PWA_TIMELINE_BUILD
+  const long long t_kernel_start = clock64();
+#endif
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NKT = kN + p.I;
   const int NKR = kN + 128;                        // rows allocated for key-side operands (prompt block issued as M = 128)
@@ -238,6 +241,12 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       *reinterpret_cast<uint4*>(Qa + c * (kN * 16) + n * 16) = *reinterpret_cast<const uint4*>(tmp);
     }
   }
+  // (bias tables of this head through shared memory: the gradient accumulators gth_s / gtw_s / gtok_s are free until the
+  //  end of the kernel and are zeroed again below)
+  for (int i = tid; i < p.wh * p.wh; i += kThreadsB) gth_s[i] = p.th[head * p.wh * p.wh + i];
+  for (int i = tid; i < p.ww * p.ww; i += kThreadsB) gtw_s[i] = p.tw[head * p.ww * p.ww + i];
+  for (int i = tid; i < p.I; i += kThreadsB) gtok_s[i] = p.tok[head * p.I + i];
+  __syncthreads();
   for (int j = tid; j < NKT; j += kThreadsB) {
     const bool content = j < kN;
     const int jw = (j / p.wd) % p.ww, jh = j / (p.wd * p.ww);
@@ -249,16 +258,20 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         const int col = c * 8 + e;
         float v = 0.f;
         if (content) {
-          if (col < p.wh) v = p.th[(head * p.wh + col) * p.wh + jh];
-          else if (col - p.wh < p.ww) v = p.tw[(head * p.ww + (col - p.wh)) * p.ww + jw];
+          if (col < p.wh) v = gth_s[col * p.wh + jh];
+          else if (col - p.wh < p.ww) v = gtw_s[(col - p.wh) * p.ww + jw];
         } else if (col < p.wh) {
-          v = p.tok[head * p.I + (j - kN)];
+          v = gtok_s[j - kN];
         }
         tmp[e] = __float2bfloat16(v * inv_scale);
       }
       *reinterpret_cast<uint4*>(Ka + c * (NKR * 16) + j * 16) = *reinterpret_cast<const uint4*>(tmp);
     }
   }
+  __syncthreads();
+  for (int i = tid; i < p.wh * p.wh; i += kThreadsB) gth_s[i] = 0.f;
+  for (int i = tid; i < p.ww * p.ww; i += kThreadsB) gtw_s[i] = 0.f;
+  for (int i = tid; i < p.I + 4; i += kThreadsB) gtok_s[i] = 0.f;
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bar[bFullS + i], 1);
@@ -298,6 +311,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   const int tlb = tid == 0 ? 0 : (tid == kIssue0 * 32 ? 2048 : (tid == (kIssue0 + 1) * 32 ? 4096 : (tid == 256 ? 8192 :
                   (tid == (kIssue0 + 4) * 32 ? 10240 : 6144))));
 #define STAMP(tag) do { if (rec && tli < 1000) { tl[tlb + 2 * tli] = clock64(); tl[tlb + 2 * tli + 1] = (tag); ++tli; } } while (0)
+  if (rec && tid == 0) { tl[16000] = t_kernel_start; tl[16001] = clock64(); }   // kernel entry, end of the per-CTA setup
 #else
 #define STAMP(tag) do { } while (0)
 #endif
@@ -513,6 +527,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     // dKaug[key][u] = sum over all rows/windows of g * onehot: columns [0,wh) -> dTh[u][jh(key)], [wh,wh+ww) -> dTw[u][jw(key)];
     // for prompt keys the wh replicated columns sum to dtok[i].  The /scale of K'aug and the *scale of dS cancel.
     // (the last dKaug chain retired with the last key block: bDoneC counts all three chains)
+    STAMP(150);                                                    // end of the window loop
     if (it > 0 && grp == n_groups - 1) {
       for (int kb = wg; kb < n_kb; kb += 2) {
         uint32_t o[16];
@@ -520,11 +535,30 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         tmem_wait_ld();
         const int key = kb * 128 + lane_row;
         if (kb < 2) {
+          // 32-way same-address shared atomics (a CAS loop each) made this reduction 38 K clk per CTA: reduce over the
+          // lanes that share a table entry by shuffles first.  With ww * wd == 32 a warp's keys share jh and every 4
+          // consecutive lanes share jw; other window shapes keep the plain atomics.
           const int jw = (key / p.wd) % p.ww, jh = key / (p.wd * p.ww);
+          const bool fast = p.ww * p.wd == 32 && p.wd == 4;
 #pragma unroll
           for (int c = 0; c < 16; ++c) {
-            if (c < p.wh) atomicAdd(&gth_s[c * p.wh + jh], __uint_as_float(o[c]));
-            else if (c - p.wh < p.ww) atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], __uint_as_float(o[c]));
+            float v = __uint_as_float(o[c]);
+            if (c < p.wh) {
+              if (fast) {
+                v = warp_sum(v);
+                if (lane == 0) atomicAdd(&gth_s[c * p.wh + jh], v);
+              } else {
+                atomicAdd(&gth_s[c * p.wh + jh], v);
+              }
+            } else if (c - p.wh < p.ww) {
+              if (fast) {
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                if ((lane & 3) == 0) atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
+              } else {
+                atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
+              }
+            }
           }
         } else if (lane_row < p.I) {
           float t = 0.f;
@@ -539,8 +573,17 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         for (int kb = 0; kb < 2; ++kb) {
           const int jd = (kb * 128 + lane_row) % p.wd;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            if (u < p.wd) atomicAdd(&gtd_s[u * p.wd + jd], acc_d[kb][u]);
+          for (int u = 0; u < 4; ++u) {
+            float v = acc_d[kb][u];
+            if (p.wd == 4) {                                         // lanes l, l+4, l+8, ... share jd
+              v += __shfl_xor_sync(0xffffffffu, v, 4);
+              v += __shfl_xor_sync(0xffffffffu, v, 8);
+              v += __shfl_xor_sync(0xffffffffu, v, 16);
+              if (lane < 4) atomicAdd(&gtd_s[u * p.wd + jd], v);
+            } else if (u < p.wd) {
+              atomicAdd(&gtd_s[u * p.wd + jd], v);
+            }
+          }
         }
       }
       comp_sync();
@@ -730,9 +773,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       STAMP(2);
     }
   }
-#undef STAMP
+  STAMP(151);                                                      // role done
   tc_fence_before();
   __syncthreads();
+  STAMP(152);                                                      // every role done
+#undef STAMP
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 

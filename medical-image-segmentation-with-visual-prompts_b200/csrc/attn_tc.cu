@@ -137,6 +137,9 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t kmax_s[4];
 
+#ifdef PWA_TIMELINE_BUILD
+  const long long t_kernel_start = clock64();
+#endif
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NKT = kN + p.I;
   const TcSmem L = tc_layout(KS, DHP, NKT, MASKED);
@@ -243,6 +246,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   int tli = 0;
   const bool rec = p.debug && p.delta != nullptr && blockIdx.x == 0 && tid == 0;
 #define STAMP(tag) do { if (rec && tli < 2000) { tl[2 * tli] = clock64(); tl[2 * tli + 1] = (tag); ++tli; } } while (0)
+  if (rec) { tl[8000] = t_kernel_start; tl[8001] = clock64(); }     // kernel entry, end of the per-CTA setup
 #else
 #define STAMP(tag) do { } while (0)
 #endif
@@ -535,6 +539,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       p.lse[((size_t)bw * p.heads + head) * kN + rown] = (mb + __log2f(l_run)) * 0.6931471805599453f;
     }
   }
+  STAMP(150);
 #undef STAMP
   tc_fence_before();
   __syncthreads();

@@ -299,19 +299,25 @@ def run_ours(args):
         # dominant kernel by accumulated device time
         dom = max(ksum.items(), key=lambda kv: kv[1][1]) if ksum else None
         roof = None
+        try:   # DRAM traffic per launch of the dominant kernel, from the committed ncu --set full capture
+            traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        except Exception:
+            traffic_tab = {}
         if dom is not None:
             name, (calls, tms, work) = dom
             if name.startswith("attn"):
                 ach = work / (tms / 1e3) / 1e12
                 roof = {"kernel": name, "bound": "tensor", "achieved": round(ach, 3), "peak": pk["tf_sus"],
-                        "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5), "traffic": None,
+                        "unit": "TFLOP/s", "frac": round(ach / pk["tf_sus"], 5),
+                        "traffic": traffic_tab.get(name, {}).get("bytes"), "traffic_of": traffic_tab.get(name, {}).get("launch"),
                         "peak_source": pk["src"] + " (sustained bf16 cuBLAS)", "avg_launch_ms": round(tms / calls, 4),
                         "share_of_step": round(tms / ms, 4),
                         "timed": "CUDA events around each launch in an eager pass of the same steps"}
             else:
                 ach = work / (tms / 1e3) / 1e9
                 roof = {"kernel": name, "bound": "hbm", "achieved": round(ach, 1), "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": round(ach / pk["hbm"], 5), "traffic": None, "peak_source": pk["src"],
+                        "frac": round(ach / pk["hbm"], 5), "traffic": traffic_tab.get(name, {}).get("bytes"),
+                        "traffic_of": traffic_tab.get(name, {}).get("launch"), "peak_source": pk["src"],
                         "avg_launch_ms": round(tms / calls, 4), "share_of_step": round(tms / ms, 4)}
         kern = {}
         for name, (calls, tms, work) in ksum.items():

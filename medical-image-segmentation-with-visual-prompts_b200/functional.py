@@ -346,6 +346,55 @@ class _AddLayerNorm(torch.autograd.Function):
                 None if dbx is None else dbx.to(bx_dt), None if dbr is None else dbr.to(br_dt))
 
 
+class _LayerNormPass(torch.autograd.Function):
+    """(x_alias, y) with y = LayerNorm(x) and x_alias = x (same storage): for an x that is ALSO consumed as a residual
+    further down (the block's shortcut, swin_block.py:215-222).  Routing that second use through x_alias lets the backward
+    add its gradient inside the LayerNorm-backward kernel (`dres`) instead of a separate full-size add pass."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous()
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        y = torch.empty_like(x)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        with torch.cuda.device(x.device), _timed("ln_fwd", 1, 2.0 * x.numel() * x.element_size(), x):
+            rc = _lib.lib.pwa_ln_fwd(_ptr(x), None, _ptr(g32), _ptr(b32), None, _ptr(y), _ptr(mean), _ptr(rstd), rows, Cc, float(eps),
+                                     _dtype_code(x), _stream(x))
+        _lib.check(rc, "pwa_ln_fwd")
+        ctx.save_for_backward(x, g32, mean, rstd)
+        ctx.param_dtypes = (gamma.dtype, beta.dtype)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, dalias, dy):
+        x, g32, mean, rstd = ctx.saved_tensors
+        Cc = x.shape[-1]
+        rows = x.numel() // Cc
+        if dy is None:
+            return dalias, None, None, None
+        dy = dy.contiguous()
+        dalias = dalias.contiguous() if dalias is not None else None
+        dx = torch.empty_like(x)
+        dg = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        db = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        nbytes = (3 if dalias is None else 4) * x.numel() * x.element_size()
+        with torch.cuda.device(x.device), _timed("ln_bwd", 1, float(nbytes), x):
+            rc = _lib.lib.pwa_ln_bwd2(_ptr(dy), _ptr(x), _ptr(g32), _ptr(mean), _ptr(rstd), _ptr(dalias), _ptr(dx), _ptr(dg), _ptr(db),
+                                      None, None, rows, Cc, _dtype_code(x), _stream(x))
+        _lib.check(rc, "pwa_ln_bwd")
+        gd, bd = ctx.param_dtypes
+        return dx, dg.to(gd), db.to(bd), None
+
+
+def layer_norm_with_passthrough(x, gamma, beta, eps: float = 1e-6):
+    """(x_alias, LayerNorm(x)); use x_alias wherever x is needed again (see _LayerNormPass)."""
+    _require_cuda(x, gamma, beta)
+    return _LayerNormPass.apply(x, gamma, beta, eps)
+
+
 def layer_norm(x, gamma, beta, eps: float = 1e-6):
     """LayerNorm over the last axis on the pwa kernel (C % 4 == 0, C <= 1024)."""
     _require_cuda(x, gamma, beta)

@@ -162,7 +162,9 @@ class SwinTransformerBlock(nn.Module):
         lowp = self._lowp_weights(cdt)
         if PF.layer_norm_supported(c):
             # pwa LayerNorm kernels (csrc/ln.cu); the `+ shortcut` of :222 is fused into mlp_norm
-            tokens = PF.layer_norm(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
+            # (xw is needed again as the shortcut: its second use goes through the alias, so that both of its gradients
+            #  are summed inside the LayerNorm-backward kernel)
+            xw, tokens = PF.layer_norm_with_passthrough(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
             prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6) \
                 if p is not None else None
             # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway

@@ -274,57 +274,9 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
     __nv_bfloat16 extra[4];
     float qn2[2];
     float kmax2 = 0.f;
-    constexpr int kKR = 3;                                 // key rows per thread: N + I <= 3 * 128
-    // all global loads of the window in flight before the first use (the masked variant is at its 128-register cap:
-    // batching spills there and measured 8 % slower)
-    constexpr bool kBatch = DH <= 24 && !MASKED;
-    if constexpr (kBatch) {
-      __nv_bfloat16 qrow[2][DH], krow[kKR][DH], vrow[kKR][DH];
-#pragma unroll
-      for (int t = 0; t < 2; ++t)
-        load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + t * kRows + tid) * p.ldq + head * DH, qrow[t]);
-#pragma unroll
-      for (int u = 0; u < kKR; ++u) {
-        const int j = u * kRows + tid;
-        if (j < NKT) {
-          const bool content = j < kN;
-          const size_t off = content ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
-          load_row<DH>((const __nv_bfloat16*)(content ? p.k : p.kp) + off, krow[u]);
-          load_row<DH>((const __nv_bfloat16*)(content ? p.v : p.vp) + off, vrow[u]);
-        }
-      }
-#pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const int n = t * kRows + tid;
-        qn2[t] = sumsq<DH>(qrow[t]);
-        const int id_ = n % p.wd;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
-        store_chunks<DH, KS>(Qs, kN * 16, n, qrow[t], extra, p.wd);
-      }
-#pragma unroll
-      for (int u = 0; u < kKR; ++u) {
-        const int j = u * kRows + tid;
-        if (j < NKT) {
-          const bool content = j < kN;
-          kmax2 = fmaxf(kmax2, sumsq<DH>(krow[u]));
-          const int jd = j % p.wd;
-#pragma unroll
-          for (int x = 0; x < 4; ++x)
-            extra[x] = (content && x < p.wd) ? __float2bfloat16(td_s[x * p.wd + jd] * inv_scale) : zero;
-          store_chunks<DH, KS>(Ks, NKT * 16, j, krow[u], extra, p.wd);
-#pragma unroll
-          for (int dc = 0; dc < NDC; ++dc) {
-            __align__(16) __nv_bfloat16 tmp[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              tmp[e] = (dc * 8 + e < DH) ? vrow[u][dc * 8 + e < DH ? dc * 8 + e : 0] : (dc * 8 + e == DH ? one : zero);
-            *reinterpret_cast<uint4*>(Vs + (j >> 3) * (NDC * 128) + dc * 128 + (j & 7) * 16) =
-                *reinterpret_cast<const uint4*>(tmp);
-          }
-        }
-      }
-    } else {
+    // (issuing all global loads of the window before their first use was measured: staging 5.8 K -> 4.2 K clk, but the
+    //  48 extra live registers push the kernel over its 128-register cap and the spills cost more than that)
+    {
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
       const int n = t * kRows + tid;

@@ -501,8 +501,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
           STAMP(109);
         }
       }
-      // ---- all key blocks done: dQ' tiles (group 1 finishes the last unit: its warpgroup w drains query tile w) ----
-      if (grp == n_groups - 1) {
+      // ---- all key blocks done: dQ' tiles (warpgroup w drains query tile w).  Group 0 takes this drain: group 1 carries
+      // the three accumulator drains of the window and was measured ~6 K clk late into the next window, which stalls
+      // both groups (its odd units gate the buffer recycling); group 0 would only be waiting at this point ----
+      if (grp == 0) {
         const int qt_last = it * n_kb * 2 + n_kb * 2 - 1;
         for (int q = qt_last - GSB + 1; q <= qt_last; ++q) mbar_wait(&bar[bDoneQ + q % GSB], (q / GSB) & 1);   // not yet awaited
         tc_fence_after();

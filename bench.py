@@ -178,7 +178,8 @@ def run_ours(args):
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     B = args.batch
-    model, plist = build_encoder(dev, attn_drop=args.dropout, proj_drop=args.dropout)
+    model, plist = build_encoder(dev, use_checkpoint=args.checkpoint, attn_drop=args.dropout,
+                                 proj_drop=0.0 if args.checkpoint else args.dropout)
     params = list(model.parameters()) + list(plist.parameters())
     c0, _, d0 = stage_specs()[0]
     gen = torch.Generator().manual_seed(1234 + rank)
@@ -336,7 +337,7 @@ def run_ours(args):
                        "per_gpu_batch": B, "global_batch": B * world, "patch": PATCH, "parallelism": f"dp{world}",
                        "l2": "per-step working set (>1 GB of activations) exceeds the 126 MB L2; inputs rotate",
                        "launch": "eager" if graphed is None else "whole step (fwd+loss+bwd) replayed as one CUDA graph",
-                       "dropout": args.dropout},
+                       "dropout": args.dropout, "use_checkpoint": bool(args.checkpoint)},
             "e2e": {"value": round(e2e_v, 4), "unit": UNIT,
                     "h2d_bytes_per_step": host[0].numel() * host[0].element_size(), "d2h_bytes_per_step": 4},
             "gpu_launches": launches,
@@ -426,6 +427,9 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.0,
                     help="attn_drop = proj_drop of the blocks (the reference's example config uses 0.1; the headline number is "
                          "measured without dropout, like the parity tests)")
+    ap.add_argument("--checkpoint", action="store_true",
+                    help="use_checkpoint=True as in the reference's example config (activation recomputation; with --dropout only "
+                         "attn_drop is applied, torch's proj_drop cannot be recomputed inside a graph capture)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the HBM-resident timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")

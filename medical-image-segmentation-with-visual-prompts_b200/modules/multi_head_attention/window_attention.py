@@ -44,11 +44,12 @@ class WindowAttention(nn.Module):
 
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias: Optional[BiasTables] = None,
                 mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None, lowp: Optional[dict] = None,
-                proj_bias_grad: bool = True):
+                proj_bias_grad: bool = True, drop_seed: Optional[torch.Tensor] = None):
         """q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
         appended to the keys/values of every window; pos_bias: BiasTables; mask: uint8 region ids [P,N]
         (mask[p,i,j] = ids[p,i]==ids[p,j]) or None; lowp: optional {'qkv','kv','proj'} weights already cast to the
-        compute dtype (SwinTransformerBlock packs them once per forward).  Returns [B,P,N,C]."""
+        compute dtype (SwinTransformerBlock packs them once per forward); drop_seed: optional int32 [2] device tensor
+        with the attention-dropout seed words (drawn here when absent).  Returns [B,P,N,C]."""
         if pos_bias is None or not isinstance(pos_bias, BiasTables):
             raise NotImplementedError("WindowAttention on the fused kernels takes the compact BiasTables form of the "
                                       "position bias (RelativePE.tables), not a dense [1,1,h,N',N'] tensor")
@@ -65,7 +66,7 @@ class WindowAttention(nn.Module):
             kvp = PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight, lowp=lp.get('kv')) \
                 if prompts is not None else None
             o = PF.prompted_window_attention_packed(qkv, kvp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
-                                                    self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop)
+                                                    self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop, seed=drop_seed)
         else:
             qq = PF.multi_linear(q, None, self.to_q.weight)
             kk = PF.multi_linear(k, None, self.to_k.weight)
@@ -75,6 +76,6 @@ class WindowAttention(nn.Module):
                 kp = PF.multi_linear(prompts, None, self.to_k.weight)
                 vp = PF.multi_linear(prompts, None, self.to_v.weight)
             o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok,
-                                             mask, self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop)
+                                             mask, self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop, seed=drop_seed)
         o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'), bias_grad=proj_bias_grad)
         return self.proj_drop(o)

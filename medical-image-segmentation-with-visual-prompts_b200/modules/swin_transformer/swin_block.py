@@ -74,7 +74,7 @@ class ConsecutiveSwinBlocks(nn.Module):
                                       merge_last_dim=merge_last_dim)
 
     def _token_pipeline_ok(self, x):
-        if not x.is_cuda or self.use_checkpoint or x.dim() != 5:
+        if not x.is_cuda or x.dim() != 5:
             return False
         # block-level hooks must keep firing: fall back to calling the blocks one by one
         mods = list(self.swin_blocks) + ([self.merge] if self.down else [])
@@ -94,9 +94,9 @@ class ConsecutiveSwinBlocks(nn.Module):
         cdt, in_dtype = blk0._compute_dtype(x), x.dtype
         with torch.autocast('cuda', enabled=False):
             tok = _partition_any(x.to(cdt), g0)
-            y, m = blk0._tokens_forward(tok, p[0], g0, cdt)
+            y, m = blk0._tokens_forward_ckpt(tok, p[0], g0, cdt)
             tok = PF.gather_rows(y, m, rowmap_regroup(g0, g1)).view(x.shape[0], g1.P, g1.N, x.shape[1])
-            y, m = blk1._tokens_forward(tok, p[1], g1, cdt)
+            y, m = blk1._tokens_forward_ckpt(tok, p[1], g1, cdt)
             if self.down:
                 out = self.merge.forward_tokens(y, m, g1)
             else:
@@ -151,7 +151,7 @@ class SwinTransformerBlock(nn.Module):
             w = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight, a.proj.weight, self.mlp.weight], dim=0).to(cdt)
         return {'qkv': w[:3 * c], 'kv': w[c:3 * c], 'proj': w[3 * c:4 * c], 'mlp': w[4 * c:]}
 
-    def _tokens_forward(self, xw, p, geom, cdt):
+    def _tokens_forward(self, xw, p, geom, cdt, drop_seed=None):
         """Window tokens [B,P,N,C] (= shortcut) -> (y, m) with block output tokens = y + m  (reference :215-227);
         the last add is left to the consumer (window reverse / regroup / PatchMerging gather fuse it)."""
         ws = tuple(self.window_size)
@@ -172,7 +172,7 @@ class SwinTransformerBlock(nn.Module):
             # skip their own bias reductions.  Only valid without projection dropout between proj and the add.
             fuse_db = not (self.training and self.attn.proj_drop.p > 0)
             a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                          prompts=prompts, lowp=lowp, proj_bias_grad=not fuse_db)
+                          prompts=prompts, lowp=lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
             y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
                                      bias_of_x=self.attn.proj.bias if fuse_db else None,
                                      bias_of_res=self.mlp.bias if fuse_db else None)
@@ -183,11 +183,28 @@ class SwinTransformerBlock(nn.Module):
             tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)
             prompts = F.layer_norm(p.to(cdt), (c,), nw, nb, 1e-6) if p is not None else None
             y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                          prompts=prompts, lowp=lowp)
+                          prompts=prompts, lowp=lowp, drop_seed=drop_seed)
             y = y + xw
             z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
         m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'])
         return y, m
+
+    def _tokens_forward_ckpt(self, xw, p, geom, cdt):
+        """_tokens_forward, under activation checkpointing when `use_checkpoint` is set (reference :257-260).  The
+        attention-dropout seed words are drawn OUTSIDE the checkpointed region and passed in, so the recomputation sees
+        the same mask without saving / restoring the CUDA generator state (which a graph capture cannot do); only
+        torch's own proj_drop needs the generator state preserved."""
+        if not (self.use_checkpoint and torch.is_grad_enabled()):
+            return self._tokens_forward(xw, p, geom, cdt)
+        seed = None
+        if self.training and self.attn.attn_drop.p > 0:
+            seed = PF.new_dropout_seed(xw.device)
+        need_rng = self.training and self.attn.proj_drop.p > 0
+        if need_rng and torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("use_checkpoint with proj_drop > 0 cannot be captured into a CUDA graph: the recomputation "
+                               "needs the generator state restored (capture without checkpointing, or set proj_drop = 0)")
+        return checkpoint.checkpoint(self._tokens_forward, xw, p, geom, cdt, seed, use_reentrant=False,
+                                     preserve_rng_state=need_rng)
 
     def _geometry(self, dims):
         shift_cfg = tuple(self.shift_size) if self.shift_size is not None else (0, 0, 0)

@@ -596,3 +596,29 @@ def test_stage_shapes_of_128_cubed_patches():
     assert rel_linf(y16, y32) < 2 * RTOL_BF16                    # two blocks + merge in bf16 end to end
     y16.float().square().mean().backward()
     assert torch.isfinite(xb.grad.float()).all()
+
+
+def test_checkpointed_token_pipeline_with_dropout_matches_plain():
+    """use_checkpoint (reference :257-260; the example config sets it) inside the token pipeline, with attention dropout:
+    the recomputation must see the same dropout masks, so outputs are bit-identical and gradients agree."""
+    from tests.util import load_npz
+    d = load_npz("pair_merge")
+    tag = "mld1"
+    sd = {k[len(tag) + 4:]: torch.from_numpy(v) for k, v in d.items() if k.startswith(tag + ".sd.")}
+    x0 = torch.from_numpy(d[f"{tag}.x"]).to(DEV)
+    p0, p1 = torch.from_numpy(d[f"{tag}.p0"]).to(DEV), torch.from_numpy(d[f"{tag}.p1"]).to(DEV)
+    res = []
+    for ckpt in (False, True):
+        pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=12, num_heads=2, pos_bias_embed_dim=16, max_prompts=1,
+                                              tokens_per_prompt=8, window_size=(4, 4, 2), down=True, merge_last_dim=True,
+                                              use_checkpoint=ckpt, attn_drop=0.2)
+        pair.load_state_dict(sd)
+        pair.to(DEV).train()
+        x = x0.clone().requires_grad_(True)
+        torch.manual_seed(11)
+        y = pair(x, (p0, p1))
+        y.square().sum().backward()
+        res.append((y.detach().clone(), x.grad.clone(), pair.swin_blocks[1].attn.to_v.weight.grad.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    for a, b in zip(res[0][1:], res[1][1:]):
+        assert rel_linf(b, a) < 1e-5

@@ -188,6 +188,11 @@ int pwa_ln_bwd2(const void* dy, const void* x, const float* gamma, const float* 
                 const void* dres, void* dx, float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
                 int64_t rows, int C, int dtype, void* stream);
 
+/* Test infrastructure only: with PWA_TIMELINE=1 in the environment and a library built with `make TIMELINE=1`, CTA 0 of
+ * the tcgen05 forward kernel records clock64 stamps; this copies them to the host (tools/timeline_fwd.py).  Returns the
+ * number of bytes copied, 0 when no timeline exists. */
+int pwa_debug_fwd_timeline(void* host_dst, int bytes);
+
 /* 1 iff the bf16 tcgen05 kernel supports this shape (else impl=0 falls back to the fp32-math kernel). */
 int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype);
 

@@ -79,7 +79,7 @@ lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
                     "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
-                    "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
+                    "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_debug_fwd_timeline", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 
 def check(rc: int, what: str):

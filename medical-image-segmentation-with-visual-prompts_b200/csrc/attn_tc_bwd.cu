@@ -45,12 +45,12 @@ using namespace tc;
 namespace {
 
 constexpr int kN = 256;
-constexpr int kThreadsB = 768;
+constexpr int kThreadsB = 800;
 constexpr int kCompute = 256;     // compute threads per group: group 0 = warps 0-7 (even units), group 1 = warps 8-15 (odd units)
 constexpr int kGroups = 2;
 constexpr int kIssue0 = kGroups * 8;   // first MMA-issuer warp (S, V, K, A, Q)
 constexpr int kProd0 = kIssue0 + 5;    // first staging warp
-constexpr int kProd = 96;         // staging threads (3 warps)
+constexpr int kProd = 128;        // service threads (4 warps, one per TMEM lane quadrant): staging + accumulator drains
 constexpr int kIds = 28;          // region ids 0..26 and 100 (-> 27), see pwa_region_ids
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -179,10 +179,11 @@ enum {
   bDoneC = 3,      // [3] dV / dK' / dKaug chains of a unit retired (three commits, count 3)
   bReady = 6,      // [3] packed P^T / g^T of a unit written        (256 compute threads)
   bDoneQ = 9,      // [2] dQ' chain of a query tile retired         (commit)
-  bAccFree = 11,   // dV / dK' accumulators of a key block drained  (256)
-  bDqFree = 12,    // dQ' accumulators of a window drained          (256)
-  bOpFull = 13,    // [2] operand buffer staged                     (96 staging threads)
-  bOpFree = 15,    // [2] operand buffer no longer needed           (256)
+  bAccFree = 11,   // dV / dK' accumulators of a key block drained  (128 service threads)
+  bDqFree = 12,    // dQ' accumulators of a window drained          (128)
+  bOpFull = 13,    // [2] operand buffer staged                     (128)
+  bKbDone = 15,    // all three accumulation chains of a key block retired (three commits, count 3)
+  bWinQ = 16,      // every dQ' chain of a window retired            (commit)
   kNumBars = 17
 };
 
@@ -281,10 +282,11 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bar[bDoneQ + i], 1);
       mbar_init(&bar[bOpFull + i], kProd);
-      mbar_init(&bar[bOpFree + i], kCompute);
     }
-    mbar_init(&bar[bAccFree], kCompute);
-    mbar_init(&bar[bDqFree], kCompute);
+    mbar_init(&bar[bAccFree], kProd);
+    mbar_init(&bar[bDqFree], kProd);
+    mbar_init(&bar[bKbDone], 3);
+    mbar_init(&bar[bWinQ], 1);
     fence_mbar_init();
   }
   fence_proxy_async_smem();
@@ -327,11 +329,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     const int wg = (warp >> 2) & 1;
     const int lane_row = tid & 127;                  // TMEM lane owned by this thread (key in S^T, row in dQ)
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float acc_d[2][4];                               // dTd contributions of this thread's keys
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int u = 0; u < 4; ++u) acc_d[a][u] = 0.f;
     int it = 0;
     for (int bw = bw0; bw < n_pairs && grp < n_groups; bw += stride, ++it) {
       const int b = bw / p.P;
@@ -446,154 +443,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         tc_fence_before();
         mbar_arrive(&bar[bReady + buf]);
         STAMP(103);
-        if (u == 3) {
-          // ---- key block done: drain dV (warpgroup 0) and dK' (warpgroup 1) ----
-          mbar_wait(&bar[bDoneC + buf], par);
-          tc_fence_after();
-          STAMP(108);
-          const int key = kb * 128 + lane_row;
-          const bool key_ok = lane_row < nk;
-          if (wg == 0) {
-            float dv[DHP];
-#pragma unroll
-            for (int dq = 0; dq < DHP / 16; ++dq) {
-              uint32_t o[16];
-              tmem_ld16(trow + cDV + dq * 16, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int d = 0; d < 16; ++d) dv[dq * 16 + d] = __uint_as_float(o[d]);
-            }
-            tc_fence_before();
-            mbar_arrive(&bar[bAccFree]);
-            if (key_ok) {
-              if (kb < 2) {
-                store_row_b<DH>((__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH, dv, keep_scale);
-              } else {
-                float* gp = p.dvp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
-#pragma unroll
-                for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dv[d] * keep_scale);
-              }
-            }
-          } else {
-            float dk[DKC];
-#pragma unroll
-            for (int dq = 0; dq < DKC / 16; ++dq) {
-              uint32_t o[16];
-              tmem_ld16(trow + cDK + dq * 16, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int d = 0; d < 16; ++d) dk[dq * 16 + d] = __uint_as_float(o[d]);
-            }
-            tc_fence_before();
-            mbar_arrive(&bar[bAccFree]);
-            if (key_ok) {
-              if (kb < 2) {
-                store_row_b<DH>((__nv_bfloat16*)p.dk + ((size_t)bw * kN + key) * p.ldq + head * DH, dk, p.scale);
-#pragma unroll
-                for (int uu = 0; uu < 4; ++uu) acc_d[kb][uu] += dk[DH + uu];   // d K'[DH+u] = sum_rows(id==u) g = dTd[u][jd]
-              } else {
-                float* gp = p.dkp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
-#pragma unroll
-                for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dk[d] * p.scale);
-              }
-            }
-          }
-          STAMP(109);
-        }
       }
-      // ---- all key blocks done: dQ' tiles (warpgroup w drains query tile w).  Group 0 takes this drain: group 1 carries
-      // the three accumulator drains of the window and was measured ~6 K clk late into the next window, which stalls
-      // both groups (its odd units gate the buffer recycling); group 0 would only be waiting at this point ----
-      if (grp == 0) {
-        const int qt_last = it * n_kb * 2 + n_kb * 2 - 1;
-        for (int q = qt_last - GSB + 1; q <= qt_last; ++q) mbar_wait(&bar[bDoneQ + q % GSB], (q / GSB) & 1);   // not yet awaited
-        tc_fence_after();
-        float dq[DKC];
-#pragma unroll
-        for (int c = 0; c < DKC / 16; ++c) {
-          uint32_t o[16];
-          tmem_ld16(trow + cDQ + wg * DKC + c * 16, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int d = 0; d < 16; ++d) dq[c * 16 + d] = __uint_as_float(o[d]);
-        }
-        tc_fence_before();
-        mbar_arrive(&bar[bDqFree]);
-        mbar_arrive(&bar[bOpFree + ob]);
-        store_row_b<DH>((__nv_bfloat16*)p.dq + ((size_t)bw * kN + wg * 128 + lane_row) * p.ldq + head * DH, dq, p.scale);
-        STAMP(4);
-      }
-    }
-
-    // ---- once per CTA: bias-table gradients ----
-    // dKaug[key][u] = sum over all rows/windows of g * onehot: columns [0,wh) -> dTh[u][jh(key)], [wh,wh+ww) -> dTw[u][jw(key)];
-    // for prompt keys the wh replicated columns sum to dtok[i].  The /scale of K'aug and the *scale of dS cancel.
-    // (the last dKaug chain retired with the last key block: bDoneC counts all three chains)
-    STAMP(150);                                                    // end of the window loop
-    if (it > 0 && grp == n_groups - 1) {
-      for (int kb = wg; kb < n_kb; kb += 2) {
-        uint32_t o[16];
-        tmem_ld16(trow + cAUG + kb * 16, o);
-        tmem_wait_ld();
-        const int key = kb * 128 + lane_row;
-        if (kb < 2) {
-          // 32-way same-address shared atomics (a CAS loop each) made this reduction 38 K clk per CTA: reduce over the
-          // lanes that share a table entry by shuffles first.  With ww * wd == 32 a warp's keys share jh and every 4
-          // consecutive lanes share jw; other window shapes keep the plain atomics.
-          const int jw = (key / p.wd) % p.ww, jh = key / (p.wd * p.ww);
-          const bool fast = p.ww * p.wd == 32 && p.wd == 4;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            float v = __uint_as_float(o[c]);
-            if (c < p.wh) {
-              if (fast) {
-                v = warp_sum(v);
-                if (lane == 0) atomicAdd(&gth_s[c * p.wh + jh], v);
-              } else {
-                atomicAdd(&gth_s[c * p.wh + jh], v);
-              }
-            } else if (c - p.wh < p.ww) {
-              if (fast) {
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                if ((lane & 3) == 0) atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
-              } else {
-                atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
-              }
-            }
-          }
-        } else if (lane_row < p.I) {
-          float t = 0.f;
-#pragma unroll
-          for (int c = 0; c < 16; ++c)
-            if (c < p.wh) t += __uint_as_float(o[c]);
-          atomicAdd(&gtok_s[lane_row], t);
-        }
-      }
-      if (wg == 1) {
-#pragma unroll
-        for (int kb = 0; kb < 2; ++kb) {
-          const int jd = (kb * 128 + lane_row) % p.wd;
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            float v = acc_d[kb][u];
-            if (p.wd == 4) {                                         // lanes l, l+4, l+8, ... share jd
-              v += __shfl_xor_sync(0xffffffffu, v, 4);
-              v += __shfl_xor_sync(0xffffffffu, v, 8);
-              v += __shfl_xor_sync(0xffffffffu, v, 16);
-              if (lane < 4) atomicAdd(&gtd_s[u * p.wd + jd], v);
-            } else if (u < p.wd) {
-              atomicAdd(&gtd_s[u * p.wd + jd], v);
-            }
-          }
-        }
-      }
-      comp_sync();
-      const int ct = tid - (n_groups - 1) * kCompute;
-      for (int i = ct; i < p.wh * p.wh; i += kCompute) atomicAdd(&p.dth[head * p.wh * p.wh + i], gth_s[i]);
-      for (int i = ct; i < p.ww * p.ww; i += kCompute) atomicAdd(&p.dtw[head * p.ww * p.ww + i], gtw_s[i]);
-      for (int i = ct; i < p.wd * p.wd; i += kCompute) atomicAdd(&p.dtd[head * p.wd * p.wd + i], gtd_s[i]);
-      for (int i = ct; i < p.I; i += kCompute) atomicAdd(&p.dtok[head * p.I + i], gtok_s[i]);
     }
   } else if (warp < kProd0) {
     // =============================================================================================
@@ -668,6 +518,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
               }
             }
             mma_commit(&bar[bDoneC + buf]);
+            if (u == 3) mma_commit(&bar[bKbDone]);                 // key block complete: the service warps drain dV / dK'
             STAMP(100);
           } else {
             // (every unit's barrier phase is awaited in order, so that a parity wait can never lag two phases behind)
@@ -686,6 +537,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
               mma_ss(tmem + cDQ + mt * DKC, da, db, idescDQ, (kb > 0) | (t > 0));
             }
             mma_commit(&bar[bDoneQ + gs]);
+            if (kb == n_kb - 1 && mt == 1) mma_commit(&bar[bWinQ]);  // window complete: the service warps drain dQ'
             STAMP(100);
           }
         }
@@ -693,11 +545,23 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     }
   } else {
     // =============================================================================================
-    // staging warps: global -> smem operand buffer of window `it` (one window ahead of the consumers when OPB = 2)
+    // service warps (4 warps = the four TMEM lane quadrants): stage the operands of the NEXT window (global -> smem,
+    // in four parts) and, in between, drain the accumulators of the CURRENT window: dV / dK' after every key block,
+    // dQ' at the end.  Neither compute group drains any more: the drains (~1 K clk each, after a ~1 K clk wait for the
+    // accumulation chains) sat on the critical tail of one group and, through the 3-deep S^T ring, stalled the other.
     // =============================================================================================
     const int pt = tid - kProd0 * 32;
-    int it = 0;
-    for (int bw = bw0; bw < n_pairs; bw += stride, ++it) {
+    const int lane_row = (warp & 3) * 32 + lane;                   // TMEM lane = key (dV, dK', dKaug) or query row (dQ')
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float acc_d[2][4];                                             // dTd contributions of this thread's keys
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc_d[a][u] = 0.f;
+
+    // part 0 / 1: query rows pt / pt + 128 (+ ids, dropout row states); part 2: key rows pt, pt + 128; part 3: key rows
+    // pt + 256 .. , selector table, hand-over; part < 0: everything
+    auto stage = [&](int it, int bw, int part) {
       const int b = bw / p.P, win = bw - b * p.P;
       const int ob = it % OPB;
       uint8_t* opnd = smem + L.opnd0 + ob * L.opnd_bytes;
@@ -711,12 +575,19 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       uint32_t* rs_s = reinterpret_cast<uint32_t*>(opnd + L.rs);
       uint32_t* sel_s = reinterpret_cast<uint32_t*>(opnd + L.sel);
       uint8_t* ids_s = opnd + L.ids;
-      if (it >= OPB) mbar_wait(&bar[bOpFree + ob], ((it / OPB) - 1) & 1);
-      STAMP(1);
-      if (DROP)
-        for (int m = pt; m < kN / 2; m += kProd)
-          rs_s[m] = drop_row_state(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN / 2, (uint32_t)(2 * m));
-      for (int n = pt; n < kN; n += kProd) {                       // query rows: Q', dO' (+ delta, lse)
+      const bool all = part < 0;
+      if (all || part == 0) {
+        STAMP(1);
+        if (DROP)
+          for (int m = pt; m < kN / 2; m += kProd)
+            rs_s[m] = drop_row_state(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN / 2, (uint32_t)(2 * m));
+        if (MASKED)
+          for (int i = pt; i < kN / 4; i += kProd)
+            reinterpret_cast<uint32_t*>(ids_s)[i] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[i];
+      }
+      for (int qi = 0; qi < 2; ++qi) {                             // query rows: Q', dO' (+ delta, lse)
+        if (!(all || part == qi)) continue;
+        const int n = pt + qi * kProd;
         const size_t goff = ((size_t)bw * kN + n) * p.C + head * DH;
         __nv_bfloat16 row[DH], drow[DH], orow[DH];
         load_row_b<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + n) * p.ldq + head * DH, row);
@@ -737,7 +608,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         lse2_s[n] = l2;
         wp_s[n] = __float2bfloat16(fast_exp2(-l2));
       }
-      for (int j = pt; j < NKT; j += kProd) {                      // key rows: K', V'
+      for (int ki = 0; ki < 3; ++ki) {                             // key rows: K', V'
+        if (!(all || (part == 2 && ki < 2) || (part == 3 && ki == 2))) continue;
+        const int j = pt + ki * kProd;
+        if (j >= NKT) continue;
         const bool content = j < kN;
         const size_t off = content ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
         __nv_bfloat16 row[DH], vrow[DH];
@@ -751,29 +625,200 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         store_chunks_b<DH, KS * 2>(Ks, NKR * 16, j, row, ex[0], ex[1], ex[2], ex[3]);
         store_chunks_b<DH, DHP / 8>(Vs, NKR * 16, j, vrow, FOLD ? one : zero, FOLD ? one : zero, zero, zero);
       }
-      if (MASKED) {
-        for (int i = pt; i < kN / 4; i += kProd)
-          reinterpret_cast<uint32_t*>(ids_s)[i] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[i];
-        prod_sync();
-        // PRMT selectors: word w of id slot s covers tokens 4w..4w+3 = packed pairs 2w (low half) and 2w+1 (high half);
-        // a kept bf16 takes its own bytes (nibbles 1,0 / 3,2), a masked one the bytes of the second operand (5,4 / 7,6)
-        for (int i = pt; i < kIds * (kN / 4); i += kProd) {
-          const int s = i / (kN / 4), w = i - s * (kN / 4);
-          const uint32_t idw = reinterpret_cast<const uint32_t*>(ids_s)[w];
-          uint32_t sel = 0;
+      if (all || part == 3) {
+        if (MASKED) {
+          prod_sync();                                             // ids of every service thread are in place
+          // PRMT selectors: word w of id slot s covers tokens 4w..4w+3 = packed pairs 2w (low half) and 2w+1 (high half);
+          // a kept bf16 takes its own bytes (nibbles 1,0 / 3,2), a masked one the bytes of the second operand (5,4 / 7,6)
+          for (int i = pt; i < kIds * (kN / 4); i += kProd) {
+            const int s = i / (kN / 4), w = i - s * (kN / 4);
+            const uint32_t idw = reinterpret_cast<const uint32_t*>(ids_s)[w];
+            uint32_t sel = 0;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const bool keep = id_slot((idw >> (8 * e)) & 0xffu) == s;
-            const uint32_t nib = (e & 1) ? (keep ? 0x32u : 0x76u) : (keep ? 0x10u : 0x54u);
-            sel |= nib << (((e & 1) ? 8 : 0) + ((e >> 1) ? 16 : 0));
+            for (int e = 0; e < 4; ++e) {
+              const bool keep = id_slot((idw >> (8 * e)) & 0xffu) == s;
+              const uint32_t nib = (e & 1) ? (keep ? 0x32u : 0x76u) : (keep ? 0x10u : 0x54u);
+              sel |= nib << (((e & 1) ? 8 : 0) + ((e >> 1) ? 16 : 0));
+            }
+            sel_s[i] = sel;
           }
-          sel_s[i] = sel;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive(&bar[bOpFull + ob]);
+        STAMP(2);
+      }
+    };
+
+    // dV and dK' of key block kb (this thread: key = lane_row); both accumulators are free once they are in registers
+    auto drain_kb = [&](int it, int bw, int kb) {
+      const int b = bw / p.P;
+      const int tile = it * n_kb + kb;
+      mbar_wait(&bar[bKbDone], tile & 1);
+      tc_fence_after();
+      STAMP(108);
+      const int nk = kb < 2 ? 128 : p.I;
+      const int key = kb * 128 + lane_row;
+      const bool key_ok = lane_row < nk;
+      {
+        float dv[DHP];
+#pragma unroll
+        for (int dq = 0; dq < DHP / 16; ++dq) {
+          uint32_t o[16];
+          tmem_ld16(trow + cDV + dq * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) dv[dq * 16 + d] = __uint_as_float(o[d]);
+        }
+        if (key_ok) {
+          if (kb < 2) {
+            store_row_b<DH>((__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH, dv, keep_scale);
+          } else {
+            float* gp = p.dvp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dv[d] * keep_scale);
+          }
         }
       }
-      fence_proxy_async_smem();
-      mbar_arrive(&bar[bOpFull + ob]);
-      STAMP(2);
+      {
+        float dk[DKC];
+#pragma unroll
+        for (int dq = 0; dq < DKC / 16; ++dq) {
+          uint32_t o[16];
+          tmem_ld16(trow + cDK + dq * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) dk[dq * 16 + d] = __uint_as_float(o[d]);
+        }
+        tc_fence_before();
+        mbar_arrive(&bar[bAccFree]);
+        if (key_ok) {
+          if (kb < 2) {
+            store_row_b<DH>((__nv_bfloat16*)p.dk + ((size_t)bw * kN + key) * p.ldq + head * DH, dk, p.scale);
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) acc_d[kb][uu] += dk[DH + uu];   // d K'[DH+u] = sum_rows(id==u) g = dTd[u][jd]
+          } else {
+            float* gp = p.dkp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
+#pragma unroll
+            for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dk[d] * p.scale);
+          }
+        }
+      }
+      STAMP(109);
+    };
+
+    // dQ' of the window (this thread: query rows lane_row and 128 + lane_row)
+    auto drain_q = [&](int it, int bw) {
+      mbar_wait(&bar[bWinQ], it & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        float dq[DKC];
+#pragma unroll
+        for (int c = 0; c < DKC / 16; ++c) {
+          uint32_t o[16];
+          tmem_ld16(trow + cDQ + mt * DKC + c * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) dq[c * 16 + d] = __uint_as_float(o[d]);
+        }
+        if (mt == 1) {
+          tc_fence_before();
+          mbar_arrive(&bar[bDqFree]);
+        }
+        store_row_b<DH>((__nv_bfloat16*)p.dq + ((size_t)bw * kN + mt * 128 + lane_row) * p.ldq + head * DH, dq, p.scale);
+      }
+      STAMP(4);
+    };
+
+    const int n_win = (n_pairs - bw0 + stride - 1) / stride;
+    stage(0, bw0, -1);
+    for (int it = 0; it < n_win; ++it) {
+      const int bw = bw0 + it * stride;
+      const bool has_next = it + 1 < n_win;
+      // (with one operand buffer the next window can only be staged once this one is fully drained)
+      const bool inter = has_next && OPB > 1;
+      // the first key block retires about a third into the window, the second at two thirds: half of the staging fits
+      // in front of each, and the next window's operands are complete well before this window ends
+      if (inter) {
+        stage(it + 1, bw + stride, 0);
+        stage(it + 1, bw + stride, 1);
+      }
+      drain_kb(it, bw, 0);
+      if (inter) {
+        stage(it + 1, bw + stride, 2);
+        stage(it + 1, bw + stride, 3);
+      }
+      drain_kb(it, bw, 1);
+      if (n_kb == 3) drain_kb(it, bw, 2);
+      drain_q(it, bw);
+      if (has_next && !inter) stage(it + 1, bw + stride, -1);
     }
+
+    // ---- once per CTA: bias-table gradients ----
+    // dKaug[key][u] = sum over all rows/windows of g * onehot: columns [0,wh) -> dTh[u][jh(key)], [wh,wh+ww) -> dTw[u][jw(key)];
+    // for prompt keys the wh replicated columns sum to dtok[i].  The /scale of K'aug and the *scale of dS cancel.
+    // (the last dKaug chain has retired: bKbDone counts all three chains of a key block)
+    STAMP(150);
+    for (int kb = 0; kb < n_kb; ++kb) {
+      uint32_t o[16];
+      tmem_ld16(trow + cAUG + kb * 16, o);
+      tmem_wait_ld();
+      const int key = kb * 128 + lane_row;
+      if (kb < 2) {
+        // 32-way same-address shared atomics are a CAS loop each: reduce over the lanes that share a table entry by
+        // shuffles first.  With ww * wd == 32 a warp's keys share jh and every 4 consecutive lanes share jw; other
+        // window shapes keep the plain atomics.
+        const int jw = (key / p.wd) % p.ww, jh = key / (p.wd * p.ww);
+        const bool fast = p.ww * p.wd == 32 && p.wd == 4;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float v = __uint_as_float(o[c]);
+          if (c < p.wh) {
+            if (fast) {
+              v = warp_sum(v);
+              if (lane == 0) atomicAdd(&gth_s[c * p.wh + jh], v);
+            } else {
+              atomicAdd(&gth_s[c * p.wh + jh], v);
+            }
+          } else if (c - p.wh < p.ww) {
+            if (fast) {
+              v += __shfl_xor_sync(0xffffffffu, v, 1);
+              v += __shfl_xor_sync(0xffffffffu, v, 2);
+              if ((lane & 3) == 0) atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
+            } else {
+              atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
+            }
+          }
+        }
+      } else if (lane_row < p.I) {
+        float t = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c < p.wh) t += __uint_as_float(o[c]);
+        atomicAdd(&gtok_s[lane_row], t);
+      }
+    }
+#pragma unroll
+    for (int kb = 0; kb < 2; ++kb) {
+      const int jd = (kb * 128 + lane_row) % p.wd;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float v = acc_d[kb][u];
+        if (p.wd == 4) {                                           // lanes l, l+4, l+8, ... share jd
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          if (lane < 4) atomicAdd(&gtd_s[u * p.wd + jd], v);
+        } else if (u < p.wd) {
+          atomicAdd(&gtd_s[u * p.wd + jd], v);
+        }
+      }
+    }
+    prod_sync();
+    for (int i = pt; i < p.wh * p.wh; i += kProd) atomicAdd(&p.dth[head * p.wh * p.wh + i], gth_s[i]);
+    for (int i = pt; i < p.ww * p.ww; i += kProd) atomicAdd(&p.dtw[head * p.ww * p.ww + i], gtw_s[i]);
+    for (int i = pt; i < p.wd * p.wd; i += kProd) atomicAdd(&p.dtd[head * p.wd * p.wd + i], gtd_s[i]);
+    for (int i = pt; i < p.I; i += kProd) atomicAdd(&p.dtok[head * p.I + i], gtok_s[i]);
   }
   STAMP(151);                                                      // role done
   tc_fence_before();

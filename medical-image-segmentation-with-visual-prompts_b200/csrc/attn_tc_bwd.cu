@@ -1,6 +1,6 @@
 // (c) backward of the fused prompted window attention on tcgen05 tensor cores + TMEM, bf16 I/O.
 //
-// One persistent CTA per SM (768 threads, all 512 TMEM columns) = one fixed head, walking over (sample, window)
+// One persistent CTA per SM (800 threads, all 512 TMEM columns) = one fixed head, walking over (sample, window)
 // pairs.  Everything is computed in the TRANSPOSED orientation: the 128 TMEM lanes are KEYS (one key block:
 // content 0-127, content 128-255, prompt tokens) and the TMEM columns are query rows, one UNIT = 64 rows:
 //     S^T [128k x 64r] = K'.Q'^T      dP^T [128k x 64r] = V'.dO'^T        (SS MMAs, fp32 accum in TMEM)
@@ -20,14 +20,15 @@
 // issued by different warps overlap (csrc/ubench.cu).  A clock64 timeline of the previous, barrier-synchronous
 // version showed 500 clk of MUFU work per unit against 1700 clk of exposed MMA latency, so the CTA is
 // warp-specialised and every hand-off is an mbarrier:
-//     warps 0-15  compute, two groups of 8 that ping-pong over the units (group 0: even units, group 1: odd units + all
-//                 accumulator drains; key = tid % 128, warpgroup = row half, two passes of 16 rows to stay within the
-//                 80-register budget of a 768-thread CTA): TMEM ld -> exp/mul/pack -> TMEM st + g^T to smem.  The
+//     warps 0-15  compute, two groups of 8 that ping-pong over the units (group 0: even units, group 1: odd units;
+//                 key = tid % 128, warpgroup = row half, two passes of 16 rows to stay within the register budget of an
+//                 800-thread CTA): TMEM ld -> exp/mul/pack -> TMEM st + g^T to smem.  The
 //                 waits / TMEM round trips / proxy fences of one group hide behind the exponentials of the other.
 //     warp  16    issues S^T / dP^T of unit g as soon as the chains of unit g - NBUF have consumed that buffer
 //     warps 17-19 issue the dV / dK' / dKaug chains of a unit when its packed operands are ready
 //     warp  20    issues dQ' per (key block, query tile)
-//     warps 21-23 stage the NEXT window's operands into the other half of a double buffer (global -> smem)
+//     warps 21-24 service: stage the NEXT window's operands into the other half of a double buffer (global -> smem) and
+//                 drain every accumulator of the current window (dV / dK' per key block, dQ' per window)
 // Measured (tools/timeline.py, `make TIMELINE=1`): the kernel is now bound by the tensor pipe's per-instruction cost --
 // 228 small MMAs per window at ~50 clk each whatever their N (csrc/ubench.cu), plus the stalls of five in-order
 // streams with dependent accumulations -- not by the MUFU pipe; fewer, fatter MMAs (merged dK'/dKaug chains, 128-row
@@ -176,7 +177,8 @@ __device__ __forceinline__ void comp_sync() { asm volatile("bar.sync 2, %0;" ::"
 
 enum {
   bFullS = 0,      // [3] scores of a unit complete                 (tcgen05.commit, count 1)
-  bDoneC = 3,      // [3] dV / dK' / dKaug chains of a unit retired (three commits, count 3)
+  bDoneC = 3,      // [3] dV / dK' / dKaug chains of a unit retired (three commits) and its bReady phase consumed by the
+                   //     dQ' issuer (one arrival): count 4
   bReady = 6,      // [3] packed P^T / g^T of a unit written        (256 compute threads)
   bDoneQ = 9,      // [2] dQ' chain of a query tile retired         (commit)
   bAccFree = 11,   // dV / dK' accumulators of a key block drained  (128 service threads)
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) {
       mbar_init(&bar[bFullS + i], 1);
-      mbar_init(&bar[bDoneC + i], 3);
+      mbar_init(&bar[bDoneC + i], 4);
       mbar_init(&bar[bReady + i], kCompute);
     }
     for (int i = 0; i < 2; ++i) {
@@ -296,6 +298,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
+#ifdef PWA_WATCHDOG
+  if (tid == 0 && blockIdx.x == 0) printf("pwa watchdog: bwd mbarrier base smem 0x%x (index = (addr - base) / 8)\n", smem_u32(&bar[0]));
+#endif
 
   const int n_kb = p.I > 0 ? 3 : 2;
   const int n_units = n_kb * 4;
@@ -521,8 +526,12 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             if (u == 3) mma_commit(&bar[bKbDone]);                 // key block complete: the service warps drain dV / dK'
             STAMP(100);
           } else {
-            // (every unit's barrier phase is awaited in order, so that a parity wait can never lag two phases behind)
+            // Every unit's phase is awaited in order, AND this issuer takes part in the recycling of the S^T ring: the dQ'
+            // chains are not among the commits that free a buffer, so without the arrival below the compute groups could
+            // run four units ahead of this warp (e.g. while it waits for bDqFree at a window start), bReady[buf] would
+            // complete two phases, and a parity wait two phases behind never returns (observed as a rare hang).
             mbar_wait(&bar[bReady + buf], par);
+            mbar_arrive(&bar[bDoneC + buf]);
             STAMP(10 + unit);
             if (hf == 0) continue;
             // dQ'[mt] += g[128 rows x nk keys] . K'[kb]
@@ -659,50 +668,52 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       const int nk = kb < 2 ? 128 : p.I;
       const int key = kb * 128 + lane_row;
       const bool key_ok = lane_row < nk;
-      {
-        float dv[DHP];
+      auto put_dv = [&](const float (&dv)[DHP]) {
+        if (!key_ok) return;
+        if (kb < 2) {
+          store_row_b<DH>((__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH, dv, keep_scale);
+        } else {
+          float* gp = p.dvp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
 #pragma unroll
-        for (int dq = 0; dq < DHP / 16; ++dq) {
-          uint32_t o[16];
-          tmem_ld16(trow + cDV + dq * 16, o);
-          tmem_wait_ld();
-#pragma unroll
-          for (int d = 0; d < 16; ++d) dv[dq * 16 + d] = __uint_as_float(o[d]);
+          for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dv[d] * keep_scale);
         }
-        if (key_ok) {
-          if (kb < 2) {
-            store_row_b<DH>((__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH, dv, keep_scale);
-          } else {
-            float* gp = p.dvp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
+      };
+      auto put_dk = [&](const float (&dk)[DKC]) {
+        if (!key_ok) return;
+        if (kb < 2) {
+          store_row_b<DH>((__nv_bfloat16*)p.dk + ((size_t)bw * kN + key) * p.ldq + head * DH, dk, p.scale);
 #pragma unroll
-            for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dv[d] * keep_scale);
-          }
+          for (int uu = 0; uu < 4; ++uu) acc_d[kb][uu] += dk[DH + uu];   // d K'[DH+u] = sum_rows(id==u) g = dTd[u][jd]
+        } else {
+          float* gp = p.dkp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dk[d] * p.scale);
         }
+      };
+      float dv[DHP], dk[DKC];
+#pragma unroll
+      for (int dq = 0; dq < DHP / 16; ++dq) {
+        uint32_t o[16];
+        tmem_ld16(trow + cDV + dq * 16, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) dv[dq * 16 + d] = __uint_as_float(o[d]);
       }
-      {
-        float dk[DKC];
+      // small heads: both accumulators into registers first, so that the next key block's chains can restart them
+      // before any of the global stores / prompt atomics below is issued
+      if constexpr (DHP + DKC > 64) put_dv(dv);
 #pragma unroll
-        for (int dq = 0; dq < DKC / 16; ++dq) {
-          uint32_t o[16];
-          tmem_ld16(trow + cDK + dq * 16, o);
-          tmem_wait_ld();
+      for (int dq = 0; dq < DKC / 16; ++dq) {
+        uint32_t o[16];
+        tmem_ld16(trow + cDK + dq * 16, o);
+        tmem_wait_ld();
 #pragma unroll
-          for (int d = 0; d < 16; ++d) dk[dq * 16 + d] = __uint_as_float(o[d]);
-        }
-        tc_fence_before();
-        mbar_arrive(&bar[bAccFree]);
-        if (key_ok) {
-          if (kb < 2) {
-            store_row_b<DH>((__nv_bfloat16*)p.dk + ((size_t)bw * kN + key) * p.ldq + head * DH, dk, p.scale);
-#pragma unroll
-            for (int uu = 0; uu < 4; ++uu) acc_d[kb][uu] += dk[DH + uu];   // d K'[DH+u] = sum_rows(id==u) g = dTd[u][jd]
-          } else {
-            float* gp = p.dkp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
-#pragma unroll
-            for (int d = 0; d < DH; ++d) atomicAdd(gp + d, dk[d] * p.scale);
-          }
-        }
+        for (int d = 0; d < 16; ++d) dk[dq * 16 + d] = __uint_as_float(o[d]);
       }
+      tc_fence_before();
+      mbar_arrive(&bar[bAccFree]);
+      if constexpr (DHP + DKC <= 64) put_dv(dv);
+      put_dk(dk);
       STAMP(109);
     };
 
@@ -710,22 +721,26 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     auto drain_q = [&](int it, int bw) {
       mbar_wait(&bar[bWinQ], it & 1);
       tc_fence_after();
+      float dq[2][DKC];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        float dq[DKC];
 #pragma unroll
         for (int c = 0; c < DKC / 16; ++c) {
           uint32_t o[16];
           tmem_ld16(trow + cDQ + mt * DKC + c * 16, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int d = 0; d < 16; ++d) dq[c * 16 + d] = __uint_as_float(o[d]);
+          for (int d = 0; d < 16; ++d) dq[mt][c * 16 + d] = __uint_as_float(o[d]);
         }
-        if (mt == 1) {
-          tc_fence_before();
-          mbar_arrive(&bar[bDqFree]);
-        }
-        store_row_b<DH>((__nv_bfloat16*)p.dq + ((size_t)bw * kN + mt * 128 + lane_row) * p.ldq + head * DH, dq, p.scale);
+        if constexpr (2 * DKC > 64)      // large heads: one tile at a time (registers)
+          store_row_b<DH>((__nv_bfloat16*)p.dq + ((size_t)bw * kN + mt * 128 + lane_row) * p.ldq + head * DH, dq[mt], p.scale);
+      }
+      tc_fence_before();
+      mbar_arrive(&bar[bDqFree]);
+      if constexpr (2 * DKC <= 64) {
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt)
+          store_row_b<DH>((__nv_bfloat16*)p.dq + ((size_t)bw * kN + mt * 128 + lane_row) * p.ldq + head * DH, dq[mt], p.scale);
       }
       STAMP(4);
     };

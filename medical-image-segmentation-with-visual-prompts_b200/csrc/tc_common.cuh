@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace pwa {
 namespace tc {
@@ -27,8 +28,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef PWA_WATCHDOG   // debug builds (make WATCHDOG=1): report a wait that never completes instead of hanging the GPU
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 24)) {
+      printf("pwa watchdog: block %d thread %d stuck on mbarrier smem 0x%x parity %u\n", (int)blockIdx.x, (int)threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -310,10 +310,13 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
 
   // clock64 timelines of CTA 0 (tools/timeline.py): compiled in only with -DPWA_TIMELINE_BUILD
 #ifdef PWA_TIMELINE_BUILD
+#ifndef PWA_TL_SERVICE_WARP
+#define PWA_TL_SERVICE_WARP 0      // which of the four service warps records its timeline
+#endif
   long long* tl = reinterpret_cast<long long*>(p.delta);
   int tli = 0;
   const bool rec = p.debug && blockIdx.x == 0 &&
-                   (tid == 0 || tid == kIssue0 * 32 || tid == (kIssue0 + 1) * 32 || tid == kProd0 * 32 || tid == 256 ||
+                   (tid == 0 || tid == kIssue0 * 32 || tid == (kIssue0 + 1) * 32 || tid == (kProd0 + PWA_TL_SERVICE_WARP) * 32 || tid == 256 ||
                     tid == (kIssue0 + 4) * 32);
   const int tlb = tid == 0 ? 0 : (tid == kIssue0 * 32 ? 2048 : (tid == (kIssue0 + 1) * 32 ? 4096 : (tid == 256 ? 8192 :
                   (tid == (kIssue0 + 4) * 32 ? 10240 : 6144))));
@@ -567,6 +570,25 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc_d[a][u] = 0.f;
+    // Prompt dK / dV: for small heads this thread keeps the row of its prompt token in registers over all windows of a
+    // sample and issues the global atomics once per sample instead of once per window (24 RED operations per key and
+    // window were ~5 % of the kernel and sat on the window boundary)
+    constexpr bool kRegPrompt = DH <= 12;
+    float accp_k[kRegPrompt ? DH : 1], accp_v[kRegPrompt ? DH : 1];
+#pragma unroll
+    for (int d = 0; d < (kRegPrompt ? DH : 1); ++d) accp_k[d] = accp_v[d] = 0.f;
+    int acc_b = -1;                                                // sample the register accumulators belong to
+    auto flush_prompt = [&]() {
+      if (!kRegPrompt || acc_b < 0 || lane_row >= p.I) return;
+      float* gk = p.dkp + ((size_t)acc_b * p.I + lane_row) * p.C + head * DH;
+      float* gv = p.dvp + ((size_t)acc_b * p.I + lane_row) * p.C + head * DH;
+#pragma unroll
+      for (int d = 0; d < (kRegPrompt ? DH : 1); ++d) {
+        atomicAdd(gk + d, accp_k[d]);
+        atomicAdd(gv + d, accp_v[d]);
+        accp_k[d] = accp_v[d] = 0.f;
+      }
+    };
 
     // part 0 / 1: query rows pt / pt + 128 (+ ids, dropout row states); part 2: key rows pt, pt + 128; part 3: key rows
     // pt + 256 .. , selector table, hand-over; part < 0: everything
@@ -672,6 +694,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         if (!key_ok) return;
         if (kb < 2) {
           store_row_b<DH>((__nv_bfloat16*)p.dv + ((size_t)bw * kN + key) * p.ldq + head * DH, dv, keep_scale);
+        } else if constexpr (kRegPrompt) {
+#pragma unroll
+          for (int d = 0; d < DH; ++d) accp_v[d] = fmaf(dv[d], keep_scale, accp_v[d]);
         } else {
           float* gp = p.dvp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
 #pragma unroll
@@ -684,6 +709,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
           store_row_b<DH>((__nv_bfloat16*)p.dk + ((size_t)bw * kN + key) * p.ldq + head * DH, dk, p.scale);
 #pragma unroll
           for (int uu = 0; uu < 4; ++uu) acc_d[kb][uu] += dk[DH + uu];   // d K'[DH+u] = sum_rows(id==u) g = dTd[u][jd]
+        } else if constexpr (kRegPrompt) {
+#pragma unroll
+          for (int d = 0; d < DH; ++d) accp_k[d] = fmaf(dk[d], p.scale, accp_k[d]);
         } else {
           float* gp = p.dkp + ((size_t)b * p.I + lane_row) * p.C + head * DH;
 #pragma unroll
@@ -749,6 +777,10 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     stage(0, bw0, -1);
     for (int it = 0; it < n_win; ++it) {
       const int bw = bw0 + it * stride;
+      if (bw / p.P != acc_b) {                                     // first window of another sample
+        flush_prompt();
+        acc_b = bw / p.P;
+      }
       const bool has_next = it + 1 < n_win;
       // (with one operand buffer the next window can only be staged once this one is fully drained)
       const bool inter = has_next && OPB > 1;
@@ -769,6 +801,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       if (has_next && !inter) stage(it + 1, bw + stride, -1);
     }
 
+    flush_prompt();
     // ---- once per CTA: bias-table gradients ----
     // dKaug[key][u] = sum over all rows/windows of g * onehot: columns [0,wh) -> dTh[u][jh(key)], [wh,wh+ww) -> dTw[u][jw(key)];
     // for prompt keys the wh replicated columns sum to dtok[i].  The /scale of K'aug and the *scale of dS cancel.

@@ -68,6 +68,8 @@ class GraphedStep:
             with torch.cuda.graph(self.graph):
                 self.loss = step_fn(*self.static_inputs)
             self.launches_per_replay = KernelStats.launches - launches0   # pwa kernels inside one replay
+            # the tensors every replay writes the parameter gradients into (None for parameters the step never reaches)
+            self.static_grads = [p.grad for p in self.params]
         finally:
             KernelStats.enabled, KernelStats.timing, KernelStats.launches = saved
 
@@ -80,6 +82,12 @@ class GraphedStep:
                 p.grad = None
         for t in self.static_inputs:
             t.grad = None
+
+    def bind_grads(self):
+        """Point every p.grad back at the tensor the graph writes (after code that reset or replaced p.grad, e.g.
+        optimizer.zero_grad(set_to_none=True) or an eager step in between): a replay does not touch p.grad itself."""
+        for p, g in zip(self.params, self.static_grads):
+            p.grad = g
 
     def allreduce_flat(self, group=None):
         """Average the flat gradient buffer over the data-parallel group: one NCCL all-reduce, one scale kernel."""

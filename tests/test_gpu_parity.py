@@ -622,3 +622,47 @@ def test_checkpointed_token_pipeline_with_dropout_matches_plain():
     assert torch.equal(res[0][0], res[1][0])
     for a, b in zip(res[0][1:], res[1][1:]):
         assert rel_linf(b, a) < 1e-5
+
+
+# --------------------------------------------------------------------------------------------------
+# whole-step CUDA graph
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("flat", [False, True])
+def test_graphed_step_matches_eager(flat):
+    """GraphedStep (forward + loss + backward captured once, replayed) must give the eager step's loss and gradients,
+    also on new input data, with plain and with flat-buffer gradients."""
+    from pwa_b200.graphs import GraphedStep, InputPrefetcher
+    torch.manual_seed(7)
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=48, num_heads=4, pos_bias_embed_dim=64, max_prompts=1,
+                                          tokens_per_prompt=64, window_size=(8, 8, 4), down=True).to(DEV)
+    prompts = [torch.nn.Parameter(0.2 * torch.randn(64, 48, device=DEV)) for _ in range(2)]
+    params = list(pair.parameters()) + prompts
+
+    def step(x):
+        p = tuple(t.to(x.dtype).unsqueeze(0).expand(x.shape[0], -1, -1) for t in prompts)
+        loss = pair(x, p).float().square().mean()
+        loss.backward()
+        return loss.detach()
+
+    xs = [torch.randn(2, 48, 16, 16, 8, device=DEV).bfloat16() for _ in range(3)]
+    g = GraphedStep(step, [xs[0].clone().requires_grad_(True)], params, flat_grads=flat)
+    feeder = InputPrefetcher(xs[0], DEV)
+    for x in xs[1:]:
+        feeder.prefetch(x.cpu().pin_memory())
+        loss_g = g(feeder.get()).clone()
+        grads_g = [p.grad.clone() for p in params]
+        xg_g = g.input_grads[0].clone()
+        for p in params:
+            p.grad = None
+        xe = x.clone().requires_grad_(True)
+        loss_e = step(xe)
+        assert rel_linf(loss_g, loss_e) < 1e-3
+        assert rel_linf(xg_g, xe.grad) < 2e-2
+        # atomics ordering + bf16: not bit-identical between runs; gradients that are numerically zero (e.g. 1e-8 against
+        # 1e-2 elsewhere) are compared on the scale of the largest gradient, not on their own noise
+        gmax = max(p.grad.abs().max().item() for p in params)
+        names = [n for n, _ in pair.named_parameters()] + ["prompt0", "prompt1"]
+        for n, a, p in zip(names, grads_g, params):
+            den = max(p.grad.abs().max().item(), 1e-3 * gmax)
+            assert (a - p.grad).abs().max().item() / den < 2e-2, (n, p.grad.abs().max().item(), gmax)
+        g.bind_grads()      # the eager step replaced p.grad; a replay writes the graph's own tensors

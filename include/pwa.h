@@ -119,6 +119,10 @@ typedef struct pwa_attn_shape {
   const void* seed_dev;        /* optional DEVICE pointer to two uint32 seed words that replace seed/offset: the
                                   words can be refreshed by a device-side RNG op every step, which keeps a captured
                                   CUDA graph of the step valid (host scalars would be frozen into the graph)      */
+  void* work;                  /* optional DEVICE scratch of >= 4*heads bytes (contents irrelevant, zeroed by the call on
+                                  its stream): per-head work counters of the tcgen05 forward, which then hands windows
+                                  to its CTAs dynamically instead of round-robin (CTAs sharing an SM do not progress
+                                  at the same rate).  NULL = static distribution.                                  */
 } pwa_attn_shape;
 
 /* q,k,v [B][P][N][C]; kp,vp [B][I][C] (NULL when I == 0): keys/values of the prompt tokens,

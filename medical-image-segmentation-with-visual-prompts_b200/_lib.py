@@ -27,7 +27,7 @@ class PwaAttnShape(C.Structure):
         ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("I", C.c_int32),
         ("ws", C.c_int32 * 3), ("scale", C.c_float), ("p_drop", C.c_float),
         ("seed", C.c_uint64), ("offset", C.c_uint64), ("ld_qkv", C.c_int32), ("ld_p", C.c_int32),
-        ("seed_dev", C.c_void_p),
+        ("seed_dev", C.c_void_p), ("work", C.c_void_p),
     ]
 
 

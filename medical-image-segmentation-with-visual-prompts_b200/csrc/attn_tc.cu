@@ -42,12 +42,33 @@ constexpr int kN = 256;           // content tokens per window (two query tiles,
 constexpr int kTmemCols = 128;
 constexpr int kOCol = 64;         // O accumulator lives in columns [64, 64 + DHP) of the S region
 constexpr int kIds = 28;          // region ids 0..26 and 100 (-> 27), see pwa_region_ids
+constexpr bool kBatchStaging = false;
 constexpr float kMaxBound = 40.f; // log2 units: the largest exp2 argument of a row stays within [-2*kMaxBound, ~0]
 
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+// exp2 on the FMA / ALU pipes (x <= 0): Cody-Waite split with round-to-nearest (magic-number add), degree-3 minimax
+// polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, far inside bf16's 2^-9), exponent patched in with one
+// shift-add.  B200 has 16 ex2/clk/SM; four resident CTAs keep that pipe ~80 % busy in steady state (and it is the only
+// pipe near its limit), so a fixed share of every row's logits -- kPolyPairs, a bit per packed pair of a 32-key chunk --
+// can take this path instead: ~9 issue slots on pipes with headroom against 1/16 clk of MUFU.
+// Measured at enc0: 4/16 of the pairs = no change (270 us), 6/16 +2 %, 8/16 +8 %: the kernel is not bound by the MUFU
+// pipe alone, so the share is 0 by default (-DPWA_POLY_PAIRS=0x8888 etc. to re-measure).
+#ifndef PWA_POLY_PAIRS
+#define PWA_POLY_PAIRS 0x0u
+#endif
+constexpr uint32_t kPolyPairs = PWA_POLY_PAIRS;
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -125.f);
+  const float t = x + 12582912.f;                  // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);            // [-0.5, 0.5]
+  float q = fmaf(0.05517132f, f, 0.24261054f);
+  q = fmaf(q, f, 0.69326097f);
+  q = fmaf(q, f, 0.99992812f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
 }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   uint32_t d;
@@ -60,6 +81,7 @@ template <int DH> struct Cfg {
   static constexpr int DHP = (DH + 1 + 15) / 16 * 16;      // V / O width (PV MMA N) incl. the ones column at DH
   static constexpr int NDC = DHP / 8;                      // 16-byte chunks per V row
   static constexpr int KS = (DH + 4 + 15) / 16;            // k-steps of the staged [q | onehot_d] operand
+  static constexpr int NACC = 64 / DHP;                    // independent O accumulators in TMEM columns [64, 128)
 };
 
 struct TcSmem {
@@ -131,7 +153,7 @@ __device__ __forceinline__ void store_chunks(uint8_t* base, uint32_t chunk_strid
 // same bf16 values the MMA consumes, and the inverse keep rate is applied once in the epilogue.
 template <int DH, bool MASKED, bool DROP>
 __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) attn_fwd_tc_kernel(AttnParams p) {
-  constexpr int DHP = Cfg<DH>::DHP, NDC = Cfg<DH>::NDC, KS = Cfg<DH>::KS;
+  constexpr int DHP = Cfg<DH>::DHP, NDC = Cfg<DH>::NDC, KS = Cfg<DH>::KS, NACC = Cfg<DH>::NACC;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -221,7 +243,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
     }
   }
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bar, 4);       // lane 0 of each of the four warps arrives (commit or plain arrive) per MMA group
     fence_mbar_init();
   }
   __syncwarp();
@@ -233,8 +255,12 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 lanes
   uint32_t phase = 0;
 
-  const uint32_t idescS128 = make_idesc_bf16(128, 128, 0, 0);
-  const uint32_t idescSP = make_idesc_bf16(128, p.I > 0 ? p.I : 16, 0, 0);
+  // One thread issues a tcgen05.mma every ~100 clk whatever its shape (csrc/ubench.cu), streams of different warps
+  // overlap: every MMA group of a step is split over the four warps (lane 0 of each issues its share and commits;
+  // the step's mbarrier expects four arrivals).  S: 32-key column slices; O: k-steps round-robin over NACC accumulators.
+  const bool split_prompt = p.I > 0 && (p.I / 4) % 16 == 0;
+  const uint32_t idescS32 = make_idesc_bf16(128, 32, 0, 0);
+  const uint32_t idescSP = make_idesc_bf16(128, p.I > 0 ? (split_prompt ? p.I / 4 : p.I) : 16, 0, 0);
   const uint32_t idescPV = make_idesc_bf16(128, DHP, 0, 1);
   const int n_kb = p.I > 0 ? 3 : 2;
   const int n_pairs = p.B * p.P;
@@ -251,55 +277,66 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
 #define STAMP(tag) do { } while (0)
 #endif
 
-  // S = Q'.K'^T for (query tile mt, key block kb); single thread
+  // S = Q'.K'^T for (query tile mt, key block kb); called by lane 0 of every warp
   auto issue_s = [&](int mt, int kb) {
     tc_fence_after();
-    const uint32_t idesc = kb < 2 ? idescS128 : idescSP;
+    int k0;
+    uint32_t idesc;
+    if (kb < 2) { k0 = warp * 32; idesc = idescS32; }
+    else if (split_prompt) { k0 = warp * (p.I / 4); idesc = idescSP; }
+    else if (warp == 0) { k0 = 0; idesc = idescSP; }
+    else { mbar_arrive(&bar); return; }
+    const uint32_t koff = (uint32_t)(kb * 128 + k0) * 16;
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
       const uint64_t da = make_smem_desc(smem_u32(Qs) + ks * 2 * (kN * 16) + mt * (kRows * 16), kN * 16, 128);
-      const uint64_t db = make_smem_desc(smem_u32(Ks) + ks * 2 * (NKT * 16) + kb * (128 * 16), NKT * 16, 128);
-      mma_ss(tmem, da, db, idesc, ks > 0);
+      const uint64_t db = make_smem_desc(smem_u32(Ks) + ks * 2 * (NKT * 16) + koff, NKT * 16, 128);
+      mma_ss(tmem + k0, da, db, idesc, ks > 0);
     }
     const uint64_t da = make_smem_desc(smem_u32(Qa) + mt * (kRows * 16), kN * 16, 128);
-    const uint64_t db = make_smem_desc(smem_u32(Ka) + kb * (128 * 16), NKT * 16, 128);
-    mma_ss(tmem, da, db, idesc, 1);
+    const uint64_t db = make_smem_desc(smem_u32(Ka) + koff, NKT * 16, 128);
+    mma_ss(tmem + k0, da, db, idesc, 1);
     mma_commit(&bar);
   };
 
-  for (int bw = blockIdx.x / p.heads; bw < n_pairs; bw += stride) {
+  // Window distribution: the first one is static, every further one comes from this head's counter (p.work) -- CTAs
+  // that share an SM do not progress at the same rate (warp scheduling is not fair between them), and with a static
+  // split the slow ones ran on alone at the end with the SM's pipes mostly idle.  The counter is read one window ahead.
+  __shared__ int next_s[2];
+  for (int bw = blockIdx.x / p.heads, it = 0; bw < n_pairs; ++it) {
     const int b = bw / p.P, win = bw - b * p.P;
+    if (tid == 0) next_s[it & 1] = p.work ? stride + (int)atomicAdd(p.work + head, 1u) : bw + stride;
     STAMP(1);
     // ---- stage this (window, head): Q, K (content + prompt rows), [V | 1], region ids ----
     __nv_bfloat16 extra[4];
     float qn2[2];
     float kmax2 = 0.f;
-    // (issuing all global loads of the window before their first use was measured: staging 5.8 K -> 4.2 K clk, but the
-    //  48 extra live registers push the kernel over its 128-register cap and the spills cost more than that)
-    {
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
+    // Global-load round trips are what staging costs (~1-2 K clk each while three other CTAs keep the SM busy).
+    // kBatchStaging: two batches -- every Q and K row of this thread in flight at once, then every V row -- instead of
+    // one round trip per row (all eight rows at once needs 48 live registers and spilled at the 128-register cap).
+    // Measured: staging 9.8 K -> 7.1 K clk per window, kernel time unchanged to +4 % (the SM is bound by the MUFU pipe
+    // shared by its four CTAs, not by one CTA's latency), so it stays off.
+    auto stage_q = [&](int t, const __nv_bfloat16 (&row)[DH]) {
       const int n = t * kRows + tid;
-      __nv_bfloat16 row[DH];
-      load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + n) * p.ldq + head * DH, row);
       qn2[t] = sumsq<DH>(row);
       const int id_ = n % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
       store_chunks<DH, KS>(Qs, kN * 16, n, row, extra, p.wd);
-    }
-    for (int j = tid; j < NKT; j += kRows) {
+    };
+    auto kv_off = [&](int j) {
+      return j < kN ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
+    };
+    auto stage_k = [&](int j, const __nv_bfloat16 (&row)[DH]) {
       const bool content = j < kN;
-      const size_t off = content ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
-      __nv_bfloat16 row[DH];
-      load_row<DH>((const __nv_bfloat16*)(content ? p.k : p.kp) + off, row);
       kmax2 = fmaxf(kmax2, sumsq<DH>(row));
       const int jd = j % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u)
         extra[u] = (content && u < p.wd) ? __float2bfloat16(td_s[u * p.wd + jd] * inv_scale) : zero;
       store_chunks<DH, KS>(Ks, NKT * 16, j, row, extra, p.wd);
-      load_row<DH>((const __nv_bfloat16*)(content ? p.v : p.vp) + off, row);
+    };
+    auto stage_v = [&](int j, const __nv_bfloat16 (&row)[DH]) {
 #pragma unroll
       for (int dc = 0; dc < NDC; ++dc) {
         __align__(16) __nv_bfloat16 tmp[8];
@@ -308,7 +345,45 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         *reinterpret_cast<uint4*>(Vs + (j >> 3) * (NDC * 128) + dc * 128 + (j & 7) * 16) =
             *reinterpret_cast<const uint4*>(tmp);
       }
-    }
+    };
+    if constexpr (kBatchStaging && DH <= 12) {
+      constexpr int KR = 3;                                      // key rows per thread: NKT <= 384 (I <= 128)
+      __nv_bfloat16 qrow[2][DH], krow[KR][DH];
+#pragma unroll
+      for (int t = 0; t < 2; ++t)
+        load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + t * kRows + tid) * p.ldq + head * DH, qrow[t]);
+#pragma unroll
+      for (int i = 0; i < KR; ++i) {
+        const int j = i * kRows + tid;
+        if (j < NKT) load_row<DH>((const __nv_bfloat16*)(j < kN ? p.k : p.kp) + kv_off(j), krow[i]);
+      }
+#pragma unroll
+      for (int t = 0; t < 2; ++t) stage_q(t, qrow[t]);
+#pragma unroll
+      for (int i = 0; i < KR; ++i)
+        if (i * kRows + tid < NKT) stage_k(i * kRows + tid, krow[i]);
+#pragma unroll
+      for (int i = 0; i < KR; ++i) {
+        const int j = i * kRows + tid;
+        if (j < NKT) load_row<DH>((const __nv_bfloat16*)(j < kN ? p.v : p.vp) + kv_off(j), krow[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < KR; ++i)
+        if (i * kRows + tid < NKT) stage_v(i * kRows + tid, krow[i]);
+    } else {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        __nv_bfloat16 row[DH];
+        load_row<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + t * kRows + tid) * p.ldq + head * DH, row);
+        stage_q(t, row);
+      }
+      for (int j = tid; j < NKT; j += kRows) {
+        __nv_bfloat16 row[DH];
+        load_row<DH>((const __nv_bfloat16*)(j < kN ? p.k : p.kp) + kv_off(j), row);
+        stage_k(j, row);
+        load_row<DH>((const __nv_bfloat16*)(j < kN ? p.v : p.vp) + kv_off(j), row);
+        stage_v(j, row);
+      }
     }
     if (MASKED) {
       for (int i = tid; i < kN / 4; i += kRows)
@@ -359,7 +434,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         float mx = -1e30f;
         for (int kb = 0; kb < n_kb; ++kb) {
           const int nk = kb < 2 ? 128 : p.I;
-          if (tid == 0) issue_s(mt, kb);
+          if (lane == 0) issue_s(mt, kb);
           __syncwarp();
           mbar_wait(&bar, phase);
           phase ^= 1;
@@ -394,7 +469,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       for (int kb = 0; kb < n_kb; ++kb) {
         const int nk = kb < 2 ? 128 : p.I;
         STAMP(10 + mt * 3 + kb);
-        if (tid == 0) issue_s(mt, kb);
+        if (lane == 0) issue_s(mt, kb);
         __syncwarp();
         mbar_wait(&bar, phase);
         phase ^= 1;
@@ -410,8 +485,10 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
           uint32_t pk[16];
 #pragma unroll
           for (int g = 0; g < 16; ++g) {
-            const float p0 = fast_exp2(fmaf(__uint_as_float(r[2 * g]), c2, -mb));
-            const float p1 = fast_exp2(fmaf(__uint_as_float(r[2 * g + 1]), c2, -mb));
+            const float x0 = fmaf(__uint_as_float(r[2 * g]), c2, -mb), x1 = fmaf(__uint_as_float(r[2 * g + 1]), c2, -mb);
+            const bool poly = (kPolyPairs >> g) & 1u;
+            const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
+            const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
             pk[g] = pack_bf16(p0, p1);
           }
           if (do_mask) {
@@ -444,14 +521,19 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         __syncthreads();
         STAMP(102);
 
-        // ---- O_blk = P.[V | 1] ----
-        if (tid == 0) {
-          tc_fence_after();
-          for (int t = 0; t < nk / 16; ++t) {
-            const uint64_t dv = make_smem_desc(smem_u32(Vs) + ((kb * 128 + t * 16) >> 3) * (NDC * 128), NDC * 128, 128);
-            mma_ts(tmem + kOCol, tmem + t * 8, dv, idescPV, t > 0);
+        // ---- O_blk = P.[V | 1]: k-step t goes to accumulator t % NACC, issued by warp t % NACC ----
+        const int nt = nk / 16;
+        if (lane == 0) {
+          if (warp < NACC && warp < nt) {
+            tc_fence_after();
+            for (int t = warp; t < nt; t += NACC) {
+              const uint64_t dv = make_smem_desc(smem_u32(Vs) + ((kb * 128 + t * 16) >> 3) * (NDC * 128), NDC * 128, 128);
+              mma_ts(tmem + kOCol + warp * DHP, tmem + t * 8, dv, idescPV, t >= NACC);
+            }
+            mma_commit(&bar);
+          } else {
+            mbar_arrive(&bar);
           }
-          mma_commit(&bar);
         }
         __syncwarp();
         mbar_wait(&bar, phase);
@@ -460,12 +542,21 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         STAMP(103);
 #pragma unroll
         for (int dq = 0; dq < DHP / 16; ++dq) {
-          uint32_t o[16];
-          tmem_ld16(trow + kOCol + dq * 16, o);
-          tmem_wait_ld();
+          constexpr int AG = NACC >= 2 ? 2 : 1;                    // accumulators drained per tcgen05.wait::ld
 #pragma unroll
-          for (int d = 0; d < 16; ++d)
-            if (dq * 16 + d <= DH) o_run[dq * 16 + d] += __uint_as_float(o[d]);
+          for (int a0 = 0; a0 < NACC; a0 += AG) {
+            if (a0 < nt) {
+              uint32_t o[AG][16];
+#pragma unroll
+              for (int a = 0; a < AG; ++a) tmem_ld16(trow + kOCol + (a0 + a) * DHP + dq * 16, o[a]);
+              tmem_wait_ld();
+#pragma unroll
+              for (int a = 0; a < AG; ++a)
+#pragma unroll
+                for (int d = 0; d < 16; ++d)
+                  if (dq * 16 + d <= DH) o_run[dq * 16 + d] += __uint_as_float(o[a][d]);
+            }
+          }
         }
         tc_fence_before();
         __syncthreads();   // everyone has drained O / P before the next S MMA overwrites the columns
@@ -490,6 +581,8 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       }
       p.lse[((size_t)bw * p.heads + head) * kN + rown] = (mb + __log2f(l_run)) * 0.6931471805599453f;
     }
+    bw = next_s[it & 1];   // written before this window's first block barrier, read after its last one; two slots, so
+                           // that the next window's write cannot overtake a slow thread's read
   }
   STAMP(150);
 #undef STAMP
@@ -513,6 +606,7 @@ int launch_tc(const AttnParams& p, cudaStream_t st) {
   auto kern = p.drop_thresh ? (p.ids ? attn_fwd_tc_kernel<DH, true, true> : attn_fwd_tc_kernel<DH, false, true>)
                             : (p.ids ? attn_fwd_tc_kernel<DH, true, false> : attn_fwd_tc_kernel<DH, false, false>);
   PWA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.work) PWA_CUDA_OK(cudaMemsetAsync(p.work, 0, sizeof(unsigned int) * p.heads, st));
   kern<<<grid, kRows, smem, st>>>(p);
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;

@@ -219,13 +219,14 @@ def gather_rows(a: torch.Tensor, b: Optional[torch.Tensor], rowmap) -> torch.Ten
 IMPL_AUTO, IMPL_F32, IMPL_TC = 0, 1, 2
 
 
-def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0, seed_dev=None):
+def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0, seed_dev=None, work=None):
     s = _lib.PwaAttnShape()
     s.B, s.P, s.C, s.heads, s.I = B, P, Cc, heads, I
     s.ld_qkv, s.ld_p = ld_qkv, ld_p
     s.ws[0], s.ws[1], s.ws[2] = ws
     s.scale, s.p_drop, s.seed, s.offset = float(scale), float(p_drop), int(seed), int(offset)
     s.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
+    s.work = None if work is None else work.data_ptr()      # forward only: per-head window counters
     return s
 
 
@@ -240,7 +241,8 @@ class _WindowAttention(torch.autograd.Function):
         th, tw, td = th.contiguous().float(), tw.contiguous().float(), td.contiguous().float()
         out = torch.empty_like(q)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=q.device)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed)
+        work = torch.empty(heads, dtype=torch.int32, device=q.device)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed, work=work)
         with torch.cuda.device(q.device), _timed("attn_fwd", 1, 4.0 * B * P * N * (N + I) * Cc, q):
             rc = _lib.lib.pwa_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(kp), _ptr(vp), _ptr(th), _ptr(tw), _ptr(td),
                                        _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), C.byref(s), _dtype_code(q), impl,
@@ -494,7 +496,8 @@ class _WindowAttentionPacked(torch.autograd.Function):
         th, tw, td = th.contiguous().float(), tw.contiguous().float(), td.contiguous().float()
         out = torch.empty((B, P, N, Cc), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=qkv.device)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed)
+        work = torch.empty(heads, dtype=torch.int32, device=qkv.device)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed, work=work)
         q0 = qkv.data_ptr()
         p0 = 0 if kvp is None else kvp.data_ptr()
         vpp = C.c_void_p

@@ -42,7 +42,10 @@ constexpr int kN = 256;           // content tokens per window (two query tiles,
 constexpr int kTmemCols = 128;
 constexpr int kOCol = 64;         // O accumulator lives in columns [64, 64 + DHP) of the S region
 constexpr int kIds = 28;          // region ids 0..26 and 100 (-> 27), see pwa_region_ids
-constexpr bool kBatchStaging = false;
+#ifndef PWA_BATCH_STAGING
+#define PWA_BATCH_STAGING 0
+#endif
+constexpr bool kBatchStaging = PWA_BATCH_STAGING != 0;
 constexpr float kMaxBound = 40.f; // log2 units: the largest exp2 argument of a row stays within [-2*kMaxBound, ~0]
 
 __device__ __forceinline__ float fast_exp2(float x) {

@@ -42,14 +42,23 @@ class WindowAttention(nn.Module):
         self.proj_drop = nn.Dropout(proj_drop)
         self.impl = PF.IMPL_AUTO
 
+    def project_prompts(self, prompts: Optional[torch.Tensor], lowp: Optional[dict] = None):
+        """K|V projection of the normalised prompt tokens [B,I,C] -> [B,I,2C] (ONE [C -> 2C] GEMM; once per sample, the
+        reference projects the prompt rows of every window)."""
+        if prompts is None:
+            return None
+        return PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight, lowp=(lowp or {}).get('kv'))
+
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias: Optional[BiasTables] = None,
                 mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None, lowp: Optional[dict] = None,
-                proj_bias_grad: bool = True, drop_seed: Optional[torch.Tensor] = None):
+                proj_bias_grad: bool = True, drop_seed: Optional[torch.Tensor] = None,
+                prompt_kv: Optional[torch.Tensor] = None):
         """q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
         appended to the keys/values of every window; pos_bias: BiasTables; mask: uint8 region ids [P,N]
         (mask[p,i,j] = ids[p,i]==ids[p,j]) or None; lowp: optional {'qkv','kv','proj'} weights already cast to the
         compute dtype (SwinTransformerBlock packs them once per forward); drop_seed: optional int32 [2] device tensor
-        with the attention-dropout seed words (drawn here when absent).  Returns [B,P,N,C]."""
+        with the attention-dropout seed words (drawn here when absent); prompt_kv: `project_prompts(prompts, lowp)`
+        computed by the caller ahead of time (self-attention path only), instead of `prompts`.  Returns [B,P,N,C]."""
         if pos_bias is None or not isinstance(pos_bias, BiasTables):
             raise NotImplementedError("WindowAttention on the fused kernels takes the compact BiasTables form of the "
                                       "position bias (RelativePE.tables), not a dense [1,1,h,N',N'] tensor")
@@ -63,8 +72,7 @@ class WindowAttention(nn.Module):
             # read q|k|v as column blocks of its output (row stride 3C), prompt K/V likewise from [C -> 2C]
             lp = lowp or {}
             qkv = PF.multi_linear(q, None, self.to_q.weight, self.to_k.weight, self.to_v.weight, lowp=lp.get('qkv'))
-            kvp = PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight, lowp=lp.get('kv')) \
-                if prompts is not None else None
+            kvp = prompt_kv if prompt_kv is not None else self.project_prompts(prompts, lp)
             o = PF.prompted_window_attention_packed(qkv, kvp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
                                                     self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop, seed=drop_seed)
         else:

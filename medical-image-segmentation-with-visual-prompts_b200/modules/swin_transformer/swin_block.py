@@ -47,6 +47,35 @@ def _partition_any(x, geom):
     return PF.partition_tokens(x, geom)
 
 
+class _SideInputs:
+    """What one block's forward needs that does NOT depend on the feature map: the relative-position bias tables, the
+    five Linear weights packed in the compute dtype, and the K|V projection of the LayerNorm-ed prompt tokens.  About ten
+    launches of 2-10 us per block (and as many again in backward) that would otherwise sit serially between the big
+    kernels; `ConsecutiveSwinBlocks` computes them for both blocks on a side stream, where they overlap the partition /
+    LayerNorm / projection kernels of the main chain (a captured step keeps them as a parallel graph branch, and
+    autograd runs their backward on the same side stream).  `ready` is recorded on that stream after the last of them."""
+    __slots__ = ("tables", "lowp", "kvp", "ready")
+
+    def __init__(self, tables, lowp, kvp, ready=None):
+        self.tables, self.lowp, self.kvp, self.ready = tables, lowp, kvp, ready
+
+    def tensors(self):
+        out = [t for t in self.tables if t is not None] + [self.lowp['qkv']._base]
+        if self.kvp is not None:
+            out.append(self.kvp)
+        return out
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
+
+
 class ConsecutiveSwinBlocks(nn.Module):
     """Unshifted block, block shifted by window//2, optional PatchMerging (reference :16-71)."""
 
@@ -93,15 +122,37 @@ class ConsecutiveSwinBlocks(nn.Module):
         g0, g1 = blk0._geometry(x.shape[2:]), blk1._geometry(x.shape[2:])
         cdt, in_dtype = blk0._compute_dtype(x), x.dtype
         with torch.autocast('cuda', enabled=False):
+            side = self._side_inputs_async(x, p, cdt)
             tok = _partition_any(x.to(cdt), g0)
-            y, m = blk0._tokens_forward_ckpt(tok, p[0], g0, cdt)
+            y, m = blk0._tokens_forward_ckpt(tok, p[0], g0, cdt, side[0])
             tok = PF.gather_rows(y, m, rowmap_regroup(g0, g1)).view(x.shape[0], g1.P, g1.N, x.shape[1])
-            y, m = blk1._tokens_forward_ckpt(tok, p[1], g1, cdt)
+            y, m = blk1._tokens_forward_ckpt(tok, p[1], g1, cdt, side[1])
             if self.down:
                 out = self.merge.forward_tokens(y, m, g1)
             else:
                 out = PF.reverse_add_tokens(y, m, g1)
         return out.to(in_dtype)
+
+    def _side_inputs_async(self, x, p, cdt):
+        """_SideInputs of both blocks; under CUDA-graph capture they are enqueued on the device's side stream (forked
+        from the capturing stream here, joined by each block right before its first use of them)."""
+        main = torch.cuda.current_stream(x.device)
+        side = _side_stream(x.device)
+        if not torch.cuda.is_current_stream_capturing():
+            # launched eagerly the step is bound by the host, not by the device: a second stream only adds event and
+            # stream-switch calls (measured: 10.7 -> 13.0 ms per step); the branch pays off as a parallel graph branch
+            return [blk._side_inputs(prompt, cdt, x.shape[1]) for blk, prompt in zip(self.swin_blocks, p)]
+        side.wait_stream(main)
+        out = []
+        with torch.cuda.stream(side):
+            for blk, prompt in zip(self.swin_blocks, p):
+                si = blk._side_inputs(prompt, cdt, x.shape[1])
+                si.ready = torch.cuda.Event()
+                si.ready.record(side)
+                for t in si.tensors():
+                    t.record_stream(main)          # allocated on the side stream, consumed on the main one
+                out.append(si)
+        return out
 
     def named_parameters_body(self):
         out = [kv for blk in self.swin_blocks for kv in blk.named_parameters_body()]
@@ -151,51 +202,67 @@ class SwinTransformerBlock(nn.Module):
             w = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight, a.proj.weight, self.mlp.weight], dim=0).to(cdt)
         return {'qkv': w[:3 * c], 'kv': w[c:3 * c], 'proj': w[3 * c:4 * c], 'mlp': w[4 * c:]}
 
-    def _tokens_forward(self, xw, p, geom, cdt, drop_seed=None):
+    def _side_inputs(self, p, cdt, c):
+        """Bias tables, packed low-precision weights and the prompt K|V projection (see _SideInputs)."""
+        ws = tuple(self.window_size)
+        n_prompt = 0 if p is None else p.size(1)
+        tables = self.pe.tables(ws[0], ws[1], ws[2], n_prompt)
+        lowp = self._lowp_weights(cdt)
+        kvp = None
+        if p is not None:
+            if PF.layer_norm_supported(c):
+                prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6)
+            else:
+                prompts = F.layer_norm(p.to(cdt), (c,), self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt), 1e-6)
+            kvp = self.attn.project_prompts(prompts, lowp)
+        return _SideInputs(tables, lowp, kvp)
+
+    def _tokens_forward(self, xw, p, geom, cdt, drop_seed=None, side=None):
         """Window tokens [B,P,N,C] (= shortcut) -> (y, m) with block output tokens = y + m  (reference :215-227);
         the last add is left to the consumer (window reverse / regroup / PatchMerging gather fuse it)."""
         ws = tuple(self.window_size)
-        n_prompt = 0 if p is None else p.size(1)
-        th, tw, td, tok = self.pe.tables(ws[0], ws[1], ws[2], n_prompt)
         ids = geom.region_ids(xw.device) if geom.masked else None
         c = xw.shape[-1]
-        lowp = self._lowp_weights(cdt)
-        if PF.layer_norm_supported(c):
+        if side is None:
+            side = self._side_inputs(p, cdt, c)
+        fused_ln = PF.layer_norm_supported(c)
+        if fused_ln:
             # pwa LayerNorm kernels (csrc/ln.cu); the `+ shortcut` of :222 is fused into mlp_norm
             # (xw is needed again as the shortcut: its second use goes through the alias, so that both of its gradients
             #  are summed inside the LayerNorm-backward kernel)
             xw, tokens = PF.layer_norm_with_passthrough(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
-            prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6) \
-                if p is not None else None
+        else:
+            tokens = F.layer_norm(xw, (c,), self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt), 1e-6)
+        if side.ready is not None:
+            torch.cuda.current_stream(xw.device).wait_event(side.ready)
+        th, tw, td, tok = side.tables
+        lowp = side.lowp
+        if fused_ln:
             # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway
             # (d of the attention branch, and d of y which equals d of m: both only meet in y + m); the two Linears
             # skip their own bias reductions.  Only valid without projection dropout between proj and the add.
             fuse_db = not (self.training and self.attn.proj_drop.p > 0)
             a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                          prompts=prompts, lowp=lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
+                          prompt_kv=side.kvp, lowp=lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
             y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
                                      bias_of_x=self.attn.proj.bias if fuse_db else None,
                                      bias_of_res=self.mlp.bias if fuse_db else None)
             m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=not fuse_db)
             return y, m
-        else:
-            nw, nb = self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt)
-            tokens = F.layer_norm(xw, (c,), nw, nb, 1e-6)
-            prompts = F.layer_norm(p.to(cdt), (c,), nw, nb, 1e-6) if p is not None else None
-            y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                          prompts=prompts, lowp=lowp, drop_seed=drop_seed)
-            y = y + xw
-            z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
+        y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
+                      prompt_kv=side.kvp, lowp=lowp, drop_seed=drop_seed)
+        y = y + xw
+        z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
         m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'])
         return y, m
 
-    def _tokens_forward_ckpt(self, xw, p, geom, cdt):
+    def _tokens_forward_ckpt(self, xw, p, geom, cdt, side=None):
         """_tokens_forward, under activation checkpointing when `use_checkpoint` is set (reference :257-260).  The
         attention-dropout seed words are drawn OUTSIDE the checkpointed region and passed in, so the recomputation sees
         the same mask without saving / restoring the CUDA generator state (which a graph capture cannot do); only
         torch's own proj_drop needs the generator state preserved."""
         if not (self.use_checkpoint and torch.is_grad_enabled()):
-            return self._tokens_forward(xw, p, geom, cdt)
+            return self._tokens_forward(xw, p, geom, cdt, None, side)
         seed = None
         if self.training and self.attn.attn_drop.p > 0:
             seed = PF.new_dropout_seed(xw.device)
@@ -203,7 +270,7 @@ class SwinTransformerBlock(nn.Module):
         if need_rng and torch.cuda.is_current_stream_capturing():
             raise RuntimeError("use_checkpoint with proj_drop > 0 cannot be captured into a CUDA graph: the recomputation "
                                "needs the generator state restored (capture without checkpointing, or set proj_drop = 0)")
-        return checkpoint.checkpoint(self._tokens_forward, xw, p, geom, cdt, seed, use_reentrant=False,
+        return checkpoint.checkpoint(self._tokens_forward, xw, p, geom, cdt, seed, side, use_reentrant=False,
                                      preserve_rng_state=need_rng)
 
     def _geometry(self, dims):

@@ -283,6 +283,270 @@ __global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 8 ? 4 : (NV * EPV
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Bulk-copy variants (bf16, one 16-byte vector per lane): the register kernels above keep one row per lane group in
+// flight, i.e. 16-48 bytes per thread, and at 4 CTAs/SM (56-64 registers) that is 16-48 KB per SM -- Little's law
+// wants ~45 KB for the measured 6.6 TB/s, and the plain forward sat at 2.9 TB/s.  Here the operand tiles of a CTA
+// iteration (256/G consecutive rows = one contiguous 3-4 KB chunk per operand) are fetched by cp.async.bulk into a
+// shared-memory ring (kMaxStages / operands deep) (one elected thread, mbarrier complete_tx), which decouples the bytes in flight
+// from the register file; the lanes then read their vector from shared memory and run the same math.
+constexpr int kMaxStages = 12;     // ring depth = kMaxStages / operands (12 / 6 / 4 tiles of 3-4 KB: ~36-48 KB per CTA in flight)
+
+__device__ __forceinline__ uint32_t ln_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ln_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ln_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void ln_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ln_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void ln_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(ln_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ln_smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(ln_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void lds_vec8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  unpack2(t.x, v[0], v[1]);
+  unpack2(t.y, v[2], v[3]);
+  unpack2(t.z, v[4], v[5]);
+  unpack2(t.w, v[6], v[7]);
+}
+
+// ring of `stages` buffers, each holding `nop` operand tiles of GPB rows; tile t of this CTA = blockIdx.x + t * gridDim.x
+template <int GPB>
+struct BulkRing {
+  uint8_t* buf;
+  uint64_t* full;
+  uint32_t tile_bytes;      // GPB * C * 2
+  int nop, C, stages;
+  long rows, n_tiles;
+  const __nv_bfloat16* src[3];
+  __device__ __forceinline__ void issue(long tile, int s) const {      // one thread
+    const long row0 = tile * GPB;
+    const long left = rows - row0;
+    const uint32_t bytes = (uint32_t)(left < GPB ? left : GPB) * (uint32_t)C * 2u;
+    ln_mbar_expect_tx(&full[s], bytes * nop);
+    for (int o = 0; o < nop; ++o) bulk_g2s(buf + ((size_t)s * nop + o) * tile_bytes, src[o] + row0 * C, bytes, &full[s]);
+  }
+  __device__ __forceinline__ const __nv_bfloat16* tile(int s, int o) const {
+    return reinterpret_cast<const __nv_bfloat16*>(buf + ((size_t)s * nop + o) * tile_bytes);
+  }
+};
+
+template <int G>
+__global__ void __launch_bounds__(kLnThreads, 4) ln_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    __nv_bfloat16* __restrict__ sum_out, __nv_bfloat16* __restrict__ y,
+                                                                    float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                                    long rows, int C, float eps) {
+  using T = __nv_bfloat16;
+  constexpr int GPB = kLnThreads / G, EPV = 8;
+  extern __shared__ __align__(128) uint8_t ln_sm[];
+  __shared__ __align__(8) uint64_t full[kMaxStages];
+  const int gl = threadIdx.x % G, gr = threadIdx.x / G;
+  const int nvec = C / EPV;
+  const bool has_res = res != nullptr;
+  BulkRing<GPB> ring;
+  ring.buf = ln_sm; ring.full = full; ring.tile_bytes = (uint32_t)GPB * C * 2u; ring.nop = has_res ? 2 : 1; ring.C = C; ring.stages = kMaxStages / ring.nop;
+  ring.rows = rows; ring.n_tiles = (rows + GPB - 1) / GPB;
+  ring.src[0] = x; ring.src[1] = res; ring.src[2] = nullptr;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ring.stages; ++s) ln_mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ring.stages; ++s) {
+      const long t = blockIdx.x + (long)s * gridDim.x;
+      if (t < ring.n_tiles) ring.issue(t, s);
+    }
+  }
+  float gm[EPV], bt[EPV];
+  const bool lane_live = gl < nvec;
+  if (lane_live) {
+    loadf<EPV>(gamma + gl * EPV, gm);
+    loadf<EPV>(beta + gl * EPV, bt);
+  }
+  const float invC = 1.f / (float)C;
+  int s = 0;
+  uint32_t par = 0;
+  for (long tile = blockIdx.x; tile < ring.n_tiles; tile += gridDim.x) {
+    const long row = tile * GPB + gr;
+    const bool live = row < rows && lane_live;
+    ln_mbar_wait(&full[s], par);
+    float v[EPV], rr[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) v[e] = rr[e] = 0.f;
+    if (live) {
+      lds_vec8(ring.tile(s, 0) + gr * C + gl * EPV, v);
+      if (has_res) lds_vec8(ring.tile(s, 1) + gr * C + gl * EPV, rr);
+    }
+    __syncthreads();                                    // every lane holds its vectors: the buffer can be refilled
+    if (threadIdx.x == 0) {
+      const long nt = tile + (long)ring.stages * gridDim.x;
+      if (nt < ring.n_tiles) ring.issue(nt, s);
+    }
+    if (++s == ring.stages) { s = 0; par ^= 1u; }
+    float sum = 0.f;
+    if (live) {
+      if (has_res) {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) v[e] += rr[e];
+        // the residual sum is stored in the I/O dtype and the statistics use the STORED value
+        Vec<T, EPV>::store(sum_out + row * C + gl * EPV, v);
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) v[e] = to_f32(from_f32<T>(v[e]));
+      }
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) sum += v[e];
+    }
+    const float mean = group_sum<G>(sum) * invC;
+    float q = 0.f;
+    if (lane_live) {
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        const float d = v[e] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+    const float rstd = rsqrtf(group_sum<G>(q) * invC + eps);
+    if (live) {
+      float o[EPV];
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) o[e] = fmaf((v[e] - mean) * rstd, gm[e], bt[e]);
+      Vec<T, EPV>::store(y + row * C + gl * EPV, o);
+      if (gl == 0) {
+        mean_out[row] = mean;
+        rstd_out[row] = rstd;
+      }
+    }
+  }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kLnThreads, 3) ln_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ mean_in,
+                                                                    const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
+                                                                    __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta, float* __restrict__ dres_colsum,
+                                                                    float* __restrict__ dx_colsum, long rows, int C) {
+  using T = __nv_bfloat16;
+  constexpr int GPB = kLnThreads / G, EPV = 8;
+  extern __shared__ __align__(128) uint8_t ln_sm[];
+  __shared__ __align__(8) uint64_t full[kMaxStages];
+  const int gl = threadIdx.x % G, gr = threadIdx.x / G;
+  const int nvec = C / EPV;
+  const bool has_res = dres != nullptr;
+  const bool want_rs = dres_colsum != nullptr && has_res, want_xs = dx_colsum != nullptr;
+  BulkRing<GPB> ring;
+  ring.buf = ln_sm; ring.full = full; ring.tile_bytes = (uint32_t)GPB * C * 2u; ring.nop = has_res ? 3 : 2; ring.C = C; ring.stages = kMaxStages / ring.nop;
+  ring.rows = rows; ring.n_tiles = (rows + GPB - 1) / GPB;
+  ring.src[0] = dy; ring.src[1] = x; ring.src[2] = dres;
+  float* red = reinterpret_cast<float*>(ln_sm + (size_t)ring.stages * ring.nop * ring.tile_bytes);      // [4][C]
+  for (int i = threadIdx.x; i < 4 * C; i += kLnThreads) red[i] = 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ring.stages; ++s) ln_mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ring.stages; ++s) {
+      const long t = blockIdx.x + (long)s * gridDim.x;
+      if (t < ring.n_tiles) ring.issue(t, s);
+    }
+  }
+  const bool lane_live = gl < nvec;
+  float gm[EPV], ag[EPV], ab[EPV], ar[EPV], ax[EPV];
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) gm[e] = ag[e] = ab[e] = ar[e] = ax[e] = 0.f;
+  if (lane_live) loadf<EPV>(gamma + gl * EPV, gm);
+  const float invC = 1.f / (float)C;
+  int s = 0;
+  uint32_t par = 0;
+  for (long tile = blockIdx.x; tile < ring.n_tiles; tile += gridDim.x) {
+    const long row = tile * GPB + gr;
+    const bool live = row < rows && lane_live;
+    const float mean = row < rows ? __ldg(mean_in + row) : 0.f;
+    const float rstd = row < rows ? __ldg(rstd_in + row) : 0.f;
+    ln_mbar_wait(&full[s], par);
+    float d[EPV], xv[EPV], rs[EPV];
+#pragma unroll
+    for (int e = 0; e < EPV; ++e) d[e] = xv[e] = rs[e] = 0.f;
+    if (live) {
+      lds_vec8(ring.tile(s, 0) + gr * C + gl * EPV, d);
+      lds_vec8(ring.tile(s, 1) + gr * C + gl * EPV, xv);
+      if (has_res) lds_vec8(ring.tile(s, 2) + gr * C + gl * EPV, rs);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long nt = tile + (long)ring.stages * gridDim.x;
+      if (nt < ring.n_tiles) ring.issue(nt, s);
+    }
+    if (++s == ring.stages) { s = 0; par ^= 1u; }
+    float s1 = 0.f, s2 = 0.f;
+    if (live) {                                           // (dead lanes / rows add nothing)
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        const float xh = (xv[e] - mean) * rstd;
+        const float g = d[e] * gm[e];
+        xv[e] = xh;
+        s1 += g;
+        s2 = fmaf(g, xh, s2);
+        ag[e] = fmaf(d[e], xh, ag[e]);
+        ab[e] += d[e];
+        d[e] = g;
+      }
+    }
+    s1 = group_sum<G>(s1) * invC;
+    s2 = group_sum<G>(s2) * invC;
+    if (live) {
+      float o[EPV];
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) {
+        o[e] = rstd * (d[e] - s1 - xv[e] * s2) + rs[e];
+        ar[e] += rs[e];
+        ax[e] += o[e];
+      }
+      Vec<T, EPV>::store(dx + row * C + gl * EPV, o);
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < EPV; ++e) {
+    float a = ag[e], b = ab[e], c = ar[e], d = ax[e];
+#pragma unroll
+    for (int o = G; o < 32; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+      if (want_rs) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (want_xs) d += __shfl_xor_sync(0xffffffffu, d, o);
+    }
+    if ((threadIdx.x & 31) < G && lane_live) {
+      atomicAdd(&red[gl * EPV + e], a);
+      atomicAdd(&red[C + gl * EPV + e], b);
+      if (want_rs) atomicAdd(&red[2 * C + gl * EPV + e], c);
+      if (want_xs) atomicAdd(&red[3 * C + gl * EPV + e], d);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += kLnThreads) {
+    atomicAdd(&dgamma[i], red[i]);
+    atomicAdd(&dbeta[i], red[C + i]);
+    if (want_rs) atomicAdd(&dres_colsum[i], red[2 * C + i]);
+    if (want_xs) atomicAdd(&dx_colsum[i], red[3 * C + i]);
+  }
+}
+
 static int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return v ? atoi(v) : dflt;
@@ -317,9 +581,43 @@ static int ln_launch(bool fwd, const LnArgs& a, cudaStream_t st) {
   return PWA_OK;
 }
 
+template <int G>
+static int ln_launch_bulk(bool fwd, const LnArgs& a, cudaStream_t st) {
+  using T = __nv_bfloat16;
+  constexpr int GPB = kLnThreads / G;
+  const int nop = fwd ? (a.res ? 2 : 1) : (a.res ? 3 : 2);
+  const size_t smem = (size_t)(kMaxStages / nop) * nop * GPB * a.C * 2 + (fwd ? 0 : 4 * a.C * sizeof(float));
+  long blocks = (a.rows + GPB - 1) / GPB;
+  // (backward: 3 CTAs/SM = 85 registers, no spills; the bytes in flight no longer depend on the occupancy)
+  const long cap = 148L * (fwd ? env_int("PWA_LN_BULK_CTAS_F", 4) : env_int("PWA_LN_BULK_CTAS_B", 3));
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (fwd) {
+    PWA_CUDA_OK(cudaFuncSetAttribute(ln_fwd_bulk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ln_fwd_bulk_kernel<G><<<(unsigned)blocks, kLnThreads, smem, st>>>((const T*)a.a, (const T*)a.res, a.gamma, a.bm, (T*)a.o1,
+                                                                      (T*)a.o2, a.f1, a.f2, a.rows, a.C, a.eps);
+  } else {
+    PWA_CUDA_OK(cudaFuncSetAttribute(ln_bwd_bulk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ln_bwd_bulk_kernel<G><<<(unsigned)blocks, kLnThreads, smem, st>>>((const T*)a.a, (const T*)a.b, a.gamma, a.bm, a.rstd,
+                                                                      (const T*)a.res, (T*)a.o1, a.f1, a.f2, a.f3, a.f4, a.rows, a.C);
+  }
+  PWA_CUDA_OK(cudaGetLastError());
+  return PWA_OK;
+}
+
 template <typename T, int EPV>
 static int ln_dispatch_v(bool fwd, const LnArgs& a, cudaStream_t st) {
   const int nvec = a.C / EPV;
+  if constexpr (sizeof(T) == 2 && EPV == 8) {
+    // one vector per lane, rows contiguous: the bulk-copy kernels (PWA_LN_BULK=0 selects the register kernels)
+    static const int use_bulk = env_int("PWA_LN_BULK", 1);
+    if (use_bulk && nvec <= 32) {
+      if (nvec <= 4) return ln_launch_bulk<4>(fwd, a, st);
+      if (nvec <= 8) return ln_launch_bulk<8>(fwd, a, st);
+      if (nvec <= 16) return ln_launch_bulk<16>(fwd, a, st);
+      return ln_launch_bulk<32>(fwd, a, st);
+    }
+  }
   const int R = env_int(fwd ? "PWA_LN_RF" : "PWA_LN_RB", 1);       // rows per group per iteration (tuning knob)
 #define LN_CASE(G, NV, R) return ln_launch<T, G, NV, EPV, R>(fwd, a, st)
 #define LN_CASE_R(G)                    \

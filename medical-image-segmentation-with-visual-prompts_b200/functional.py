@@ -5,6 +5,8 @@ from __future__ import annotations
 import ctypes as C
 from typing import Optional, Sequence
 
+import functools
+
 import torch
 
 from . import _lib
@@ -575,17 +577,43 @@ def _mm_f32(a, b):
         return torch.mm(a, b).float()
 
 
+@functools.lru_cache(maxsize=None)
+def _token_split(T):
+    """Number of slices of the token axis for the batched weight-gradient GEMM: the divisor of T closest to 72 within
+    [32, 160] (0 = none)."""
+    cands = [d for d in range(32, 161) if T % d == 0]
+    return min(cands, key=lambda d: abs(d - 72)) if cands else 0
+
+
+def _wgrad(dy2, x2):
+    """dW = dy^T x in fp32, dy [T,Cout], x [T,Cin].  For the block's Linears the output is tiny (48x48 .. 288x96) and
+    T is 10^4..10^6 tokens: cuBLAS picks a split-K kernel that takes ~50 us at enc0 whatever Cout is (1.7-3.3 TB/s).
+    Slicing the token axis into ~72 batches (torch.bmm, fp32 partials, one sum) streams the operands at 4-4.8 TB/s:
+    51.7 -> 21.5 us for 48x48, 51.6 -> 35.4 us for 144x48, 16.7 -> 9.6 us for 96x96 (tools/wgrad_probe.py)."""
+    T, co = dy2.shape
+    ci = x2.shape[1]
+    if dy2.dtype != torch.float32 and T >= 16384 and co * ci <= 40960 and dy2.is_contiguous() and x2.is_contiguous():
+        S = _token_split(T)
+        if S:
+            try:
+                part = torch.bmm(dy2.view(S, T // S, co).transpose(1, 2), x2.view(S, T // S, ci), out_dtype=torch.float32)
+                return part.sum(0)
+            except (TypeError, RuntimeError):
+                pass
+    return _mm_f32(dy2.t(), x2)
+
+
 class _MultiLinear(torch.autograd.Function):
     """y = x @ cat(weights)^T (+ bias): several nn.Linear weights that share an input, as ONE GEMM."""
 
     @staticmethod
-    def forward(ctx, x, bias, lowp, bias_grad, *weights):
+    def forward(ctx, x, bias, lowp, bias_grad, lowp_bias, *weights):
         # `lowp`: the same weights already concatenated and cast to x.dtype (one cat + one cast per block instead
         # of two kernels per Linear); the fp32 master weights stay the autograd inputs
         w = lowp if lowp is not None else (weights[0] if len(weights) == 1 else torch.cat(weights, dim=0)).detach().to(x.dtype)
         x2 = x.reshape(-1, x.shape[-1])
         if bias is not None:
-            y = torch.addmm(bias.detach().to(x.dtype), x2, w.t())
+            y = torch.addmm(lowp_bias if lowp_bias is not None else bias.detach().to(x.dtype), x2, w.t())
         else:
             y = torch.mm(x2, w.t())
         ctx.save_for_backward(x2, w)
@@ -601,16 +629,17 @@ class _MultiLinear(torch.autograd.Function):
         dx = torch.mm(dy2, w).reshape(xshape) if ctx.needs_input_grad[0] else None
         db = dy2.sum(dim=0, dtype=torch.float32).to(bdt) if bdt is not None and ctx.needs_input_grad[1] else None
         dws = [None] * len(rows)
-        if any(ctx.needs_input_grad[4:]):
-            dw = _mm_f32(dy2.t(), x2)
+        if any(ctx.needs_input_grad[5:]):
+            dw = _wgrad(dy2, x2)
             o = 0
             for i, r in enumerate(rows):
-                if ctx.needs_input_grad[4 + i]:
+                if ctx.needs_input_grad[5 + i]:
                     dws[i] = dw[o:o + r].to(wdts[i])
                 o += r
-        return (dx, db, None, None, *dws)
+        return (dx, db, None, None, None, *dws)
 
 
-def multi_linear(x, bias, *weights, lowp=None, bias_grad=True):
-    """bias_grad=False: the bias gradient is produced elsewhere (add_layer_norm's fused column sums)."""
-    return _MultiLinear.apply(x, bias, lowp, bias_grad, *weights)
+def multi_linear(x, bias, *weights, lowp=None, bias_grad=True, lowp_bias=None):
+    """bias_grad=False: the bias gradient is produced elsewhere (add_layer_norm's fused column sums); lowp / lowp_bias:
+    the weights (concatenated) and the bias already cast to x.dtype."""
+    return _MultiLinear.apply(x, bias, lowp, bias_grad, lowp_bias, *weights)

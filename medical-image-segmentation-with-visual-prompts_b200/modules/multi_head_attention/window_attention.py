@@ -85,5 +85,6 @@ class WindowAttention(nn.Module):
                 vp = PF.multi_linear(prompts, None, self.to_v.weight)
             o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok,
                                              mask, self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop, seed=drop_seed)
-        o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'), bias_grad=proj_bias_grad)
+        o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'), bias_grad=proj_bias_grad,
+                            lowp_bias=(lowp or {}).get('proj_b'))
         return self.proj_drop(o)

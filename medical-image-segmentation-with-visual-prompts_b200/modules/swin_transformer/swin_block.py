@@ -194,13 +194,16 @@ class SwinTransformerBlock(nn.Module):
         return torch.float32
 
     def _lowp_weights(self, cdt):
-        """The five Linear weights of the block concatenated and cast to the compute dtype with ONE cat + ONE cast
-        (instead of a cast per Linear and call); slices: qkv [3C,C], kv [2C,C], proj [C,C], mlp [C,C]."""
+        """The five Linear weights and the two Linear biases of the block concatenated and cast to the compute dtype
+        with ONE cat + ONE cast (instead of a cast per Linear and call); slices: qkv [3C,C], kv [2C,C], proj [C,C],
+        mlp [C,C], proj_b [C], mlp_b [C]."""
         with torch.no_grad():
             a = self.attn
             c = self.mlp.weight.shape[0]
-            w = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight, a.proj.weight, self.mlp.weight], dim=0).to(cdt)
-        return {'qkv': w[:3 * c], 'kv': w[c:3 * c], 'proj': w[3 * c:4 * c], 'mlp': w[4 * c:]}
+            w = torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight, a.proj.weight, self.mlp.weight,
+                           a.proj.bias[None], self.mlp.bias[None]], dim=0).to(cdt)
+        return {'qkv': w[:3 * c], 'kv': w[c:3 * c], 'proj': w[3 * c:4 * c], 'mlp': w[4 * c:5 * c],
+                'proj_b': w[5 * c], 'mlp_b': w[5 * c + 1]}
 
     def _side_inputs(self, p, cdt, c):
         """Bias tables, packed low-precision weights and the prompt K|V projection (see _SideInputs)."""
@@ -247,13 +250,14 @@ class SwinTransformerBlock(nn.Module):
             y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
                                      bias_of_x=self.attn.proj.bias if fuse_db else None,
                                      bias_of_res=self.mlp.bias if fuse_db else None)
-            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=not fuse_db)
+            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=not fuse_db,
+                                lowp_bias=lowp['mlp_b'])
             return y, m
         y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
                       prompt_kv=side.kvp, lowp=lowp, drop_seed=drop_seed)
         y = y + xw
         z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
-        m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'])
+        m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], lowp_bias=lowp['mlp_b'])
         return y, m
 
     def _tokens_forward_ckpt(self, xw, p, geom, cdt, side=None):

@@ -135,7 +135,10 @@ class _MeanSquare(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         (x,) = ctx.saved_tensors
-        return x * (g * (2.0 / x.numel()))
+        # (a 0-dim CUDA operand sends `x * coef` down TensorIterator's strided path, 21 us at the first stage; the
+        #  multi-tensor kernel with a tensor scalar is vectorised)
+        coef = (g * (2.0 / x.numel())).to(x.dtype)
+        return torch._foreach_mul((x,), coef)[0]
 
 
 def encoder_step(model, plist, x):

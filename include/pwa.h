@@ -103,6 +103,11 @@ int pwa_reverse_add(const void* tokens_a, const void* tokens_b, void* x, int B, 
 int pwa_gather_rows(const void* src_a, const void* src_b, void* dst, const int32_t* map, int B,
                     int64_t rows_src, int64_t rows_dst, int C, int dtype, void* stream);
 
+/* dst[j] = sum over s < S of src[s][j]  (fp32, src [S][n] and dst [n] on the DEVICE).  Final reduction of the
+ * token-split weight gradients of the block's Linear layers (swin_block.py:141-143, window_attention.py:28-32;
+ * torch autograd in the reference): dW = dy^T x is computed as S batched slices of the token axis with fp32 partials. */
+int pwa_colsum_f32(const float* src, float* dst, int S, int64_t n, void* stream);
+
 /* ---- (b) fused prompted window attention, forward -------------------------------------------- */
 
 typedef struct pwa_attn_shape {

@@ -55,6 +55,8 @@ def _load():
     lib.pwa_reverse_add.restype = i32
     lib.pwa_gather_rows.argtypes = [vp, vp, vp, vp, i32, C.c_int64, C.c_int64, i32, i32, vp]
     lib.pwa_gather_rows.restype = i32
+    lib.pwa_colsum_f32.argtypes = [f32p, f32p, i32, C.c_int64, vp]
+    lib.pwa_colsum_f32.restype = i32
     lib.pwa_debug_fwd_timeline.argtypes = [vp, i32]
     lib.pwa_debug_fwd_timeline.restype = i32
     lib.pwa_attn_tc_supported.argtypes = [sp, i32]
@@ -78,7 +80,7 @@ def _load():
 lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
-                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
+                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
                     "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_debug_fwd_timeline", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 

@@ -585,6 +585,17 @@ def _token_split(T):
     return min(cands, key=lambda d: abs(d - 72)) if cands else 0
 
 
+def colsum_f32(part):
+    """[S, ...] fp32 -> [...]: sum over the leading axis on the pwa kernel (csrc/reduce.cu)."""
+    _require_cuda(part)
+    part = part.contiguous()
+    out = torch.empty(part.shape[1:], dtype=torch.float32, device=part.device)
+    with torch.cuda.device(part.device), _timed("colsum", 1, 4.0 * part.numel(), part):
+        rc = _lib.lib.pwa_colsum_f32(_ptr(part), _ptr(out), part.shape[0], out.numel(), _stream(part))
+    _lib.check(rc, "pwa_colsum_f32")
+    return out
+
+
 def _wgrad(dy2, x2):
     """dW = dy^T x in fp32, dy [T,Cout], x [T,Cin].  For the block's Linears the output is tiny (48x48 .. 288x96) and
     T is 10^4..10^6 tokens: cuBLAS picks a split-K kernel that takes ~50 us at enc0 whatever Cout is (1.7-3.3 TB/s).
@@ -597,9 +608,10 @@ def _wgrad(dy2, x2):
         if S:
             try:
                 part = torch.bmm(dy2.view(S, T // S, co).transpose(1, 2), x2.view(S, T // S, ci), out_dtype=torch.float32)
-                return part.sum(0)
             except (TypeError, RuntimeError):
-                pass
+                part = None
+            if part is not None:
+                return colsum_f32(part)
     return _mm_f32(dy2.t(), x2)
 
 

@@ -666,3 +666,31 @@ def test_graphed_step_matches_eager(flat):
             den = max(p.grad.abs().max().item(), 1e-3 * gmax)
             assert (a - p.grad).abs().max().item() / den < 2e-2, (n, p.grad.abs().max().item(), gmax)
         g.bind_grads()      # the eager step replaced p.grad; a replay writes the graph's own tensors
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("S,shape", [(72, (48, 48)), (64, (576, 192)), (1, (5,)), (33, (7, 3, 2))])
+def test_colsum_f32_matches_torch(S, shape):
+    """pwa_colsum_f32 (final sum of the token-split weight gradients) against torch.sum."""
+    from pwa_b200 import functional as PF
+    torch.manual_seed(S)
+    part = torch.randn(S, *shape, device=DEV)
+    out = PF.colsum_f32(part)
+    ref = part.double().sum(0)
+    assert out.shape == ref.shape and out.dtype == torch.float32
+    assert (out.double() - ref).abs().max().item() <= 1e-5 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,co,ci", [(72 * 512, 48, 48), (64 * 448, 144, 48), (16384 + 8, 96, 96), (1000, 48, 48)])
+def test_token_split_weight_gradient(T, co, ci):
+    """The batched token-split dW = dy^T x (bf16 operands, fp32 partials) against an fp64 GEMM; shapes that do not split
+    (no divisor of T in range, too few tokens) take the single-GEMM path."""
+    from pwa_b200 import functional as PF
+    torch.manual_seed(T)
+    dy = torch.randn(T, co, device=DEV).bfloat16()
+    x = torch.randn(T, ci, device=DEV).bfloat16()
+    dw = PF._wgrad(dy, x)
+    ref = dy.double().t() @ x.double()
+    assert dw.dtype == torch.float32 and dw.shape == (co, ci)
+    assert (dw.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()

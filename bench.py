@@ -245,15 +245,30 @@ def run_ours(args):
     from pwa_b200.graphs import InputPrefetcher
     feeder = InputPrefetcher(xdev[0], dev)
 
+    loss_host = torch.empty(2, dtype=torch.float32).pin_memory()
+    loss_events = [torch.cuda.Event(), torch.cuda.Event()]
+
     def run_e2e(n):
-        """n steps from pinned host batches: the H2D copy of step i+1 runs on a side stream while step i computes;
-        every step ends with a device -> host read of its loss."""
+        """n steps from pinned host batches: the H2D copy of step i+1 runs on a side stream while step i computes.
+        The loss of EVERY step is read on the host, one step late (as a training loop logs it): step i's loss goes to
+        pinned host memory with an asynchronous D2H copy ordered behind its graph replay, and is waited for and read
+        after step i+1 has been launched, so that the host never drains the device between steps; the last one is
+        read before the function returns (inside the timed region)."""
         feeder.prefetch(host[0])
+        total = 0.0
         for i in range(n):
             x = feeder.get()
             if i + 1 < n:
                 feeder.prefetch(host[(i + 1) % len(host)])
-            float(run_step(x).item())
+            loss = run_step(x)
+            loss_host[i % 2:i % 2 + 1].copy_(loss.reshape(1), non_blocking=True)
+            loss_events[i % 2].record()
+            if i > 0:
+                loss_events[(i - 1) % 2].synchronize()
+                total += float(loss_host[(i - 1) % 2])
+        loss_events[(n - 1) % 2].synchronize()
+        total += float(loss_host[(n - 1) % 2])
+        return total
 
     def step_eager_instrumented(i):
         zero()

@@ -343,22 +343,25 @@ struct BulkRing {
   }
 };
 
-template <int G>
-__global__ void __launch_bounds__(kLnThreads, 4) ln_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+// R rows per lane group and iteration (tile = R * 256/G rows): the per-iteration overhead (mbarrier wait, block barrier,
+// refill, addressing, loop) is paid once per R rows, and the shuffle reductions of the R rows interleave.
+template <int G, int R>
+__global__ void __launch_bounds__(kLnThreads, R == 1 ? 4 : 3) ln_fwd_bulk_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                     __nv_bfloat16* __restrict__ sum_out, __nv_bfloat16* __restrict__ y,
                                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                     long rows, int C, float eps) {
   using T = __nv_bfloat16;
-  constexpr int GPB = kLnThreads / G, EPV = 8;
+  constexpr int GPB = kLnThreads / G, TR = GPB * R, EPV = 8;
   extern __shared__ __align__(128) uint8_t ln_sm[];
   __shared__ __align__(8) uint64_t full[kMaxStages];
   const int gl = threadIdx.x % G, gr = threadIdx.x / G;
   const int nvec = C / EPV;
   const bool has_res = res != nullptr;
-  BulkRing<GPB> ring;
-  ring.buf = ln_sm; ring.full = full; ring.tile_bytes = (uint32_t)GPB * C * 2u; ring.nop = has_res ? 2 : 1; ring.C = C; ring.stages = kMaxStages / ring.nop;
-  ring.rows = rows; ring.n_tiles = (rows + GPB - 1) / GPB;
+  BulkRing<TR> ring;
+  ring.buf = ln_sm; ring.full = full; ring.tile_bytes = (uint32_t)TR * C * 2u; ring.nop = has_res ? 2 : 1; ring.C = C;
+  ring.stages = kMaxStages / ring.nop / R;
+  ring.rows = rows; ring.n_tiles = (rows + TR - 1) / TR;
   ring.src[0] = x; ring.src[1] = res; ring.src[2] = nullptr;
   if (threadIdx.x == 0) {
     for (int s = 0; s < ring.stages; ++s) ln_mbar_init(&full[s], 1);
@@ -381,15 +384,17 @@ __global__ void __launch_bounds__(kLnThreads, 4) ln_fwd_bulk_kernel(const __nv_b
   int s = 0;
   uint32_t par = 0;
   for (long tile = blockIdx.x; tile < ring.n_tiles; tile += gridDim.x) {
-    const long row = tile * GPB + gr;
-    const bool live = row < rows && lane_live;
+    const long row0 = tile * TR + gr;
     ln_mbar_wait(&full[s], par);
-    float v[EPV], rr[EPV];
+    float v[R][EPV], rr[R][EPV];
 #pragma unroll
-    for (int e = 0; e < EPV; ++e) v[e] = rr[e] = 0.f;
-    if (live) {
-      lds_vec8(ring.tile(s, 0) + gr * C + gl * EPV, v);
-      if (has_res) lds_vec8(ring.tile(s, 1) + gr * C + gl * EPV, rr);
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) v[r][e] = rr[r][e] = 0.f;
+      if (lane_live && row0 + r * GPB < rows) {
+        lds_vec8(ring.tile(s, 0) + (r * GPB + gr) * C + gl * EPV, v[r]);
+        if (has_res) lds_vec8(ring.tile(s, 1) + (r * GPB + gr) * C + gl * EPV, rr[r]);
+      }
     }
     __syncthreads();                                    // every lane holds its vectors: the buffer can be refilled
     if (threadIdx.x == 0) {
@@ -397,60 +402,76 @@ __global__ void __launch_bounds__(kLnThreads, 4) ln_fwd_bulk_kernel(const __nv_b
       if (nt < ring.n_tiles) ring.issue(nt, s);
     }
     if (++s == ring.stages) { s = 0; par ^= 1u; }
-    float sum = 0.f;
-    if (live) {
-      if (has_res) {
+    float sum[R], q[R], mean[R], rstd[R];
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) v[e] += rr[e];
-        // the residual sum is stored in the I/O dtype and the statistics use the STORED value
-        Vec<T, EPV>::store(sum_out + row * C + gl * EPV, v);
+    for (int r = 0; r < R; ++r) {
+      const long row = row0 + r * GPB;
+      const bool live = lane_live && row < rows;
+      sum[r] = 0.f;
+      if (live) {
+        if (has_res) {
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) v[e] = to_f32(from_f32<T>(v[e]));
-      }
+          for (int e = 0; e < EPV; ++e) v[r][e] += rr[r][e];
+          // the residual sum is stored in the I/O dtype and the statistics use the STORED value
+          Vec<T, EPV>::store(sum_out + row * C + gl * EPV, v[r]);
 #pragma unroll
-      for (int e = 0; e < EPV; ++e) sum += v[e];
-    }
-    const float mean = group_sum<G>(sum) * invC;
-    float q = 0.f;
-    if (lane_live) {
+          for (int e = 0; e < EPV; ++e) v[r][e] = to_f32(from_f32<T>(v[r][e]));
+        }
 #pragma unroll
-      for (int e = 0; e < EPV; ++e) {
-        const float d = v[e] - mean;
-        q = fmaf(d, d, q);
+        for (int e = 0; e < EPV; ++e) sum[r] += v[r][e];
       }
     }
-    const float rstd = rsqrtf(group_sum<G>(q) * invC + eps);
-    if (live) {
-      float o[EPV];
 #pragma unroll
-      for (int e = 0; e < EPV; ++e) o[e] = fmaf((v[e] - mean) * rstd, gm[e], bt[e]);
-      Vec<T, EPV>::store(y + row * C + gl * EPV, o);
-      if (gl == 0) {
-        mean_out[row] = mean;
-        rstd_out[row] = rstd;
+    for (int r = 0; r < R; ++r) mean[r] = group_sum<G>(sum[r]) * invC;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      q[r] = 0.f;
+      if (lane_live) {
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          const float d = v[r][e] - mean[r];
+          q[r] = fmaf(d, d, q[r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(group_sum<G>(q[r]) * invC + eps);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long row = row0 + r * GPB;
+      if (lane_live && row < rows) {
+        float o[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) o[e] = fmaf((v[r][e] - mean[r]) * rstd[r], gm[e], bt[e]);
+        Vec<T, EPV>::store(y + row * C + gl * EPV, o);
+        if (gl == 0) {
+          mean_out[row] = mean[r];
+          rstd_out[row] = rstd[r];
+        }
       }
     }
   }
 }
 
-template <int G>
-__global__ void __launch_bounds__(kLnThreads, 3) ln_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+template <int G, int R>
+__global__ void __launch_bounds__(kLnThreads, R == 1 ? 3 : 2) ln_bwd_bulk_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                                                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                                     const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dres,
                                                                     __nv_bfloat16* __restrict__ dx, float* __restrict__ dgamma,
                                                                     float* __restrict__ dbeta, float* __restrict__ dres_colsum,
                                                                     float* __restrict__ dx_colsum, long rows, int C) {
   using T = __nv_bfloat16;
-  constexpr int GPB = kLnThreads / G, EPV = 8;
+  constexpr int GPB = kLnThreads / G, TR = GPB * R, EPV = 8;
   extern __shared__ __align__(128) uint8_t ln_sm[];
   __shared__ __align__(8) uint64_t full[kMaxStages];
   const int gl = threadIdx.x % G, gr = threadIdx.x / G;
   const int nvec = C / EPV;
   const bool has_res = dres != nullptr;
   const bool want_rs = dres_colsum != nullptr && has_res, want_xs = dx_colsum != nullptr;
-  BulkRing<GPB> ring;
-  ring.buf = ln_sm; ring.full = full; ring.tile_bytes = (uint32_t)GPB * C * 2u; ring.nop = has_res ? 3 : 2; ring.C = C; ring.stages = kMaxStages / ring.nop;
-  ring.rows = rows; ring.n_tiles = (rows + GPB - 1) / GPB;
+  BulkRing<TR> ring;
+  ring.buf = ln_sm; ring.full = full; ring.tile_bytes = (uint32_t)TR * C * 2u; ring.nop = has_res ? 3 : 2; ring.C = C;
+  ring.stages = kMaxStages / ring.nop / R;
+  ring.rows = rows; ring.n_tiles = (rows + TR - 1) / TR;
   ring.src[0] = dy; ring.src[1] = x; ring.src[2] = dres;
   float* red = reinterpret_cast<float*>(ln_sm + (size_t)ring.stages * ring.nop * ring.tile_bytes);      // [4][C]
   for (int i = threadIdx.x; i < 4 * C; i += kLnThreads) red[i] = 0.f;
@@ -474,18 +495,25 @@ __global__ void __launch_bounds__(kLnThreads, 3) ln_bwd_bulk_kernel(const __nv_b
   int s = 0;
   uint32_t par = 0;
   for (long tile = blockIdx.x; tile < ring.n_tiles; tile += gridDim.x) {
-    const long row = tile * GPB + gr;
-    const bool live = row < rows && lane_live;
-    const float mean = row < rows ? __ldg(mean_in + row) : 0.f;
-    const float rstd = row < rows ? __ldg(rstd_in + row) : 0.f;
-    ln_mbar_wait(&full[s], par);
-    float d[EPV], xv[EPV], rs[EPV];
+    const long row0 = tile * TR + gr;
+    float mean[R], rstd[R];
 #pragma unroll
-    for (int e = 0; e < EPV; ++e) d[e] = xv[e] = rs[e] = 0.f;
-    if (live) {
-      lds_vec8(ring.tile(s, 0) + gr * C + gl * EPV, d);
-      lds_vec8(ring.tile(s, 1) + gr * C + gl * EPV, xv);
-      if (has_res) lds_vec8(ring.tile(s, 2) + gr * C + gl * EPV, rs);
+    for (int r = 0; r < R; ++r) {
+      const long row = row0 + r * GPB;
+      mean[r] = row < rows ? __ldg(mean_in + row) : 0.f;
+      rstd[r] = row < rows ? __ldg(rstd_in + row) : 0.f;
+    }
+    ln_mbar_wait(&full[s], par);
+    float d[R][EPV], xv[R][EPV], rs[R][EPV];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int e = 0; e < EPV; ++e) d[r][e] = xv[r][e] = rs[r][e] = 0.f;
+      if (lane_live && row0 + r * GPB < rows) {
+        lds_vec8(ring.tile(s, 0) + (r * GPB + gr) * C + gl * EPV, d[r]);
+        lds_vec8(ring.tile(s, 1) + (r * GPB + gr) * C + gl * EPV, xv[r]);
+        if (has_res) lds_vec8(ring.tile(s, 2) + (r * GPB + gr) * C + gl * EPV, rs[r]);
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -493,31 +521,42 @@ __global__ void __launch_bounds__(kLnThreads, 3) ln_bwd_bulk_kernel(const __nv_b
       if (nt < ring.n_tiles) ring.issue(nt, s);
     }
     if (++s == ring.stages) { s = 0; par ^= 1u; }
-    float s1 = 0.f, s2 = 0.f;
-    if (live) {                                           // (dead lanes / rows add nothing)
+    float s1[R], s2[R];
 #pragma unroll
-      for (int e = 0; e < EPV; ++e) {
-        const float xh = (xv[e] - mean) * rstd;
-        const float g = d[e] * gm[e];
-        xv[e] = xh;
-        s1 += g;
-        s2 = fmaf(g, xh, s2);
-        ag[e] = fmaf(d[e], xh, ag[e]);
-        ab[e] += d[e];
-        d[e] = g;
+    for (int r = 0; r < R; ++r) {
+      s1[r] = s2[r] = 0.f;
+      if (lane_live && row0 + r * GPB < rows) {             // (dead lanes / rows add nothing)
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          const float xh = (xv[r][e] - mean[r]) * rstd[r];
+          const float g = d[r][e] * gm[e];
+          xv[r][e] = xh;
+          s1[r] += g;
+          s2[r] = fmaf(g, xh, s2[r]);
+          ag[e] = fmaf(d[r][e], xh, ag[e]);
+          ab[e] += d[r][e];
+          d[r][e] = g;
+        }
       }
     }
-    s1 = group_sum<G>(s1) * invC;
-    s2 = group_sum<G>(s2) * invC;
-    if (live) {
-      float o[EPV];
 #pragma unroll
-      for (int e = 0; e < EPV; ++e) {
-        o[e] = rstd * (d[e] - s1 - xv[e] * s2) + rs[e];
-        ar[e] += rs[e];
-        ax[e] += o[e];
+    for (int r = 0; r < R; ++r) {
+      s1[r] = group_sum<G>(s1[r]) * invC;
+      s2[r] = group_sum<G>(s2[r]) * invC;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long row = row0 + r * GPB;
+      if (lane_live && row < rows) {
+        float o[EPV];
+#pragma unroll
+        for (int e = 0; e < EPV; ++e) {
+          o[e] = rstd[r] * (d[r][e] - s1[r] - xv[r][e] * s2[r]) + rs[r][e];
+          ar[e] += rs[r][e];
+          ax[e] += o[e];
+        }
+        Vec<T, EPV>::store(dx + row * C + gl * EPV, o);
       }
-      Vec<T, EPV>::store(dx + row * C + gl * EPV, o);
     }
   }
   __syncthreads();
@@ -581,28 +620,36 @@ static int ln_launch(bool fwd, const LnArgs& a, cudaStream_t st) {
   return PWA_OK;
 }
 
-template <int G>
-static int ln_launch_bulk(bool fwd, const LnArgs& a, cudaStream_t st) {
+template <int G, int R>
+static int ln_launch_bulk_r(bool fwd, const LnArgs& a, cudaStream_t st) {
   using T = __nv_bfloat16;
-  constexpr int GPB = kLnThreads / G;
+  constexpr int TR = kLnThreads / G * R;
   const int nop = fwd ? (a.res ? 2 : 1) : (a.res ? 3 : 2);
-  const size_t smem = (size_t)(kMaxStages / nop) * nop * GPB * a.C * 2 + (fwd ? 0 : 4 * a.C * sizeof(float));
-  long blocks = (a.rows + GPB - 1) / GPB;
+  const size_t smem = (size_t)(kMaxStages / nop / R) * nop * TR * a.C * 2 + (fwd ? 0 : 4 * a.C * sizeof(float));
+  long blocks = (a.rows + TR - 1) / TR;
   // (backward: 3 CTAs/SM = 85 registers, no spills; the bytes in flight no longer depend on the occupancy)
-  const long cap = 148L * (fwd ? env_int("PWA_LN_BULK_CTAS_F", 4) : env_int("PWA_LN_BULK_CTAS_B", 3));
+  const long cap = 148L * (fwd ? env_int("PWA_LN_BULK_CTAS_F", R == 1 ? 4 : 3) : env_int("PWA_LN_BULK_CTAS_B", R == 1 ? 3 : 2));
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (fwd) {
-    PWA_CUDA_OK(cudaFuncSetAttribute(ln_fwd_bulk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ln_fwd_bulk_kernel<G><<<(unsigned)blocks, kLnThreads, smem, st>>>((const T*)a.a, (const T*)a.res, a.gamma, a.bm, (T*)a.o1,
-                                                                      (T*)a.o2, a.f1, a.f2, a.rows, a.C, a.eps);
+    PWA_CUDA_OK(cudaFuncSetAttribute(ln_fwd_bulk_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ln_fwd_bulk_kernel<G, R><<<(unsigned)blocks, kLnThreads, smem, st>>>((const T*)a.a, (const T*)a.res, a.gamma, a.bm, (T*)a.o1,
+                                                                         (T*)a.o2, a.f1, a.f2, a.rows, a.C, a.eps);
   } else {
-    PWA_CUDA_OK(cudaFuncSetAttribute(ln_bwd_bulk_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    ln_bwd_bulk_kernel<G><<<(unsigned)blocks, kLnThreads, smem, st>>>((const T*)a.a, (const T*)a.b, a.gamma, a.bm, a.rstd,
-                                                                      (const T*)a.res, (T*)a.o1, a.f1, a.f2, a.f3, a.f4, a.rows, a.C);
+    PWA_CUDA_OK(cudaFuncSetAttribute(ln_bwd_bulk_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ln_bwd_bulk_kernel<G, R><<<(unsigned)blocks, kLnThreads, smem, st>>>((const T*)a.a, (const T*)a.b, a.gamma, a.bm, a.rstd,
+                                                                         (const T*)a.res, (T*)a.o1, a.f1, a.f2, a.f3, a.f4, a.rows, a.C);
   }
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
+}
+
+template <int G>
+static int ln_launch_bulk(bool fwd, const LnArgs& a, cudaStream_t st) {
+  // measured (tools/bench_ln.py): R = 2 is 8-13 % faster in backward, within +-5 % in forward
+  static const int rf = env_int("PWA_LN_BULK_RF", 1), rb = env_int("PWA_LN_BULK_RB", 2);
+  if ((fwd ? rf : rb) == 2) return ln_launch_bulk_r<G, 2>(fwd, a, st);
+  return ln_launch_bulk_r<G, 1>(fwd, a, st);
 }
 
 template <typename T, int EPV>

@@ -807,24 +807,29 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     // for prompt keys the wh replicated columns sum to dtok[i].  The /scale of K'aug and the *scale of dS cancel.
     // (the last dKaug chain has retired: bKbDone counts all three chains of a key block)
     STAMP(150);
+    // Shared-memory fp32 atomicAdd is a compare-and-swap loop (ATOMS.CAST.SPIN): ~60 of them per thread made this
+    // epilogue 20 K clk per CTA.  With ww * wd == 32 (wd == 4) every table entry has ONE writer per (key block, warp):
+    // a warp's keys share jh = 4 kb + warp, every 4 consecutive lanes share jw, lanes l, l+4, ... share jd.  So after the
+    // shuffle reduction the values go to per-(kb, warp) slots with plain stores (the g^T staging buffers are free by
+    // now) and are summed when the CTA's result is added to global memory.  Other window shapes keep the atomics.
+    const bool fast = p.ww * p.wd == 32 && p.wd == 4;
+    float* slot_w = reinterpret_cast<float*>(smem + L.g);            // [8][ww * ww]
+    float* slot_d = slot_w + 8 * p.ww * p.ww;                        // [8][wd * wd]
+    const int wq = warp & 3;
     for (int kb = 0; kb < n_kb; ++kb) {
       uint32_t o[16];
       tmem_ld16(trow + cAUG + kb * 16, o);
       tmem_wait_ld();
       const int key = kb * 128 + lane_row;
       if (kb < 2) {
-        // 32-way same-address shared atomics are a CAS loop each: reduce over the lanes that share a table entry by
-        // shuffles first.  With ww * wd == 32 a warp's keys share jh and every 4 consecutive lanes share jw; other
-        // window shapes keep the plain atomics.
         const int jw = (key / p.wd) % p.ww, jh = key / (p.wd * p.ww);
-        const bool fast = p.ww * p.wd == 32 && p.wd == 4;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           float v = __uint_as_float(o[c]);
           if (c < p.wh) {
             if (fast) {
               v = warp_sum(v);
-              if (lane == 0) atomicAdd(&gth_s[c * p.wh + jh], v);
+              if (lane == 0) gth_s[c * p.wh + jh] = v;
             } else {
               atomicAdd(&gth_s[c * p.wh + jh], v);
             }
@@ -832,7 +837,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             if (fast) {
               v += __shfl_xor_sync(0xffffffffu, v, 1);
               v += __shfl_xor_sync(0xffffffffu, v, 2);
-              if ((lane & 3) == 0) atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
+              if ((lane & 3) == 0) slot_w[(kb * 4 + wq) * p.ww * p.ww + (c - p.wh) * p.ww + jw] = v;
             } else {
               atomicAdd(&gtw_s[(c - p.wh) * p.ww + jw], v);
             }
@@ -843,29 +848,48 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
 #pragma unroll
         for (int c = 0; c < 16; ++c)
           if (c < p.wh) t += __uint_as_float(o[c]);
-        atomicAdd(&gtok_s[lane_row], t);
+        gtok_s[lane_row] = t;                                      // one key per thread
       }
     }
+    STAMP(153);
 #pragma unroll
     for (int kb = 0; kb < 2; ++kb) {
       const int jd = (kb * 128 + lane_row) % p.wd;
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         float v = acc_d[kb][u];
-        if (p.wd == 4) {                                           // lanes l, l+4, l+8, ... share jd
+        if (fast) {                                                // lanes l, l+4, l+8, ... share jd
           v += __shfl_xor_sync(0xffffffffu, v, 4);
           v += __shfl_xor_sync(0xffffffffu, v, 8);
           v += __shfl_xor_sync(0xffffffffu, v, 16);
-          if (lane < 4) atomicAdd(&gtd_s[u * p.wd + jd], v);
+          if (lane < 4) slot_d[(kb * 4 + wq) * 16 + u * 4 + jd] = v;
         } else if (u < p.wd) {
           atomicAdd(&gtd_s[u * p.wd + jd], v);
         }
       }
     }
+    STAMP(154);
     prod_sync();
+    STAMP(155);
     for (int i = pt; i < p.wh * p.wh; i += kProd) atomicAdd(&p.dth[head * p.wh * p.wh + i], gth_s[i]);
-    for (int i = pt; i < p.ww * p.ww; i += kProd) atomicAdd(&p.dtw[head * p.ww * p.ww + i], gtw_s[i]);
-    for (int i = pt; i < p.wd * p.wd; i += kProd) atomicAdd(&p.dtd[head * p.wd * p.wd + i], gtd_s[i]);
+    for (int i = pt; i < p.ww * p.ww; i += kProd) {
+      float v = gtw_s[i];
+      if (fast) {
+        v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += slot_w[k * p.ww * p.ww + i];
+      }
+      atomicAdd(&p.dtw[head * p.ww * p.ww + i], v);
+    }
+    for (int i = pt; i < p.wd * p.wd; i += kProd) {
+      float v = gtd_s[i];
+      if (fast) {
+        v = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += slot_d[k * 16 + i];
+      }
+      atomicAdd(&p.dtd[head * p.wd * p.wd + i], v);
+    }
     for (int i = pt; i < p.I; i += kProd) atomicAdd(&p.dtok[head * p.I + i], gtok_s[i]);
   }
   STAMP(151);                                                      // role done

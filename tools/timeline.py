@@ -31,7 +31,7 @@ for base, nm in names.items():
     allev += [(t, nm, tag) for t, tag in ev if 0 < tag < 200 and t > 0]
 ks, ke = int(d[16000]), int(d[16001])
 firsts = {nm: min(t for t, n2, tag in allev if n2 == nm) for nm in names.values() if any(n2 == nm for _, n2, _ in allev)}
-lasts = {nm: [(t - ks, tag) for t, n2, tag in sorted(allev) if n2 == nm][-3:] for nm in names.values()}
+lasts = {nm: [(t - ks, tag) for t, n2, tag in sorted(allev) if n2 == nm][-8:] for nm in names.values()}
 print("setup clk", ke - ks, "| first event per actor (clk after kernel entry)", {k: v - ks for k, v in firsts.items()})
 print("last events per actor", lasts)
 ca = [(t, tag) for t, nm, tag in allev if nm == "cA"]

@@ -188,14 +188,12 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus > 1 and world == 1:
-        print(json.dumps({"error": "launch with torchrun for --gpus > 1"}))
+        emit(json.dumps({"error": "launch with torchrun for --gpus > 1"}))
         return 2
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly one JSON line: NCCL's version banner / debug output goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
@@ -381,7 +379,7 @@ def run_ours(args):
             "attn_tflops": round(algorithmic_work(B * world) * args.steps / (ms / 1e3) / 1e12, 3),
             "roofline": roof, "kernels": kern, "clocks": clocks, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -448,11 +446,33 @@ def run_reference(args):
         "cpu_baseline": cpu,
         "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
     return 0
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version banner, through C stdio, whatever
+    NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the result line is written
+    to a private duplicate of the original stdout."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: str):
+    if _JSON_FD is None:
+        print(line, flush=True)
+    else:
+        os.write(_JSON_FD, (line + "\n").encode())
+
+
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

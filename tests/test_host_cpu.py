@@ -132,3 +132,14 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert key in line, key
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_token_split_picks_a_divisor_near_72():
+    """The weight-gradient GEMM slices the token axis into S batches: S divides T, lies in [32, 160] and is the divisor
+    closest to 72; 0 (= single GEMM) when no such divisor exists."""
+    from pwa_b200.functional import _token_split
+    for T in (442368, 55296, 28672, 6912, 4 * 13824, 32 * 17, 160 * 1001):
+        S = _token_split(T)
+        assert S and T % S == 0 and 32 <= S <= 160, (T, S)
+        assert all(abs(d - 72) >= abs(S - 72) for d in range(32, 161) if T % d == 0)
+    assert _token_split(1000003) == 0 and _token_split(31) == 0

@@ -1,6 +1,6 @@
 """Whole-step CUDA-graph capture for training steps built on the pwa kernels.
 
-One forward+backward of the prompted Swin encoder is ~450 kernel launches (ours + cuBLAS + a few torch
+One forward+backward of the prompted Swin encoder is ~280 kernel launches (ours + cuBLAS + a few torch
 elementwise ops), most of them 3-50 us long: launched eagerly from Python the step is bound by the host, not
 by the GPU.  Every pwa C-ABI entry point launches on the caller's stream, allocates nothing and never
 synchronises (include/pwa.h), so a whole step -- forward, loss, backward -- can be captured ONCE into a CUDA

@@ -219,6 +219,9 @@ def gather_rows(a: torch.Tensor, b: Optional[torch.Tensor], rowmap) -> torch.Ten
 # (b)/(c) fused prompted window attention
 # ------------------------------------------------------------------------------------------------
 IMPL_AUTO, IMPL_F32, IMPL_TC = 0, 1, 2
+# per-head work counters of the tcgen05 forward (pwa_attn_shape.work): True = windows are handed to the CTAs dynamically,
+# False = static round-robin.  Both distributions are parity-tested (tests/test_gpu_multiwindow.py).
+DYNAMIC_WORK = True
 
 
 def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0, seed_dev=None, work=None):
@@ -243,7 +246,7 @@ class _WindowAttention(torch.autograd.Function):
         th, tw, td = th.contiguous().float(), tw.contiguous().float(), td.contiguous().float()
         out = torch.empty_like(q)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=q.device)
-        work = torch.empty(heads, dtype=torch.int32, device=q.device)
+        work = torch.empty(heads, dtype=torch.int32, device=q.device) if DYNAMIC_WORK else None
         s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed, work=work)
         with torch.cuda.device(q.device), _timed("attn_fwd", 1, 4.0 * B * P * N * (N + I) * Cc, q):
             rc = _lib.lib.pwa_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(kp), _ptr(vp), _ptr(th), _ptr(tw), _ptr(td),
@@ -498,7 +501,7 @@ class _WindowAttentionPacked(torch.autograd.Function):
         th, tw, td = th.contiguous().float(), tw.contiguous().float(), td.contiguous().float()
         out = torch.empty((B, P, N, Cc), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=qkv.device)
-        work = torch.empty(heads, dtype=torch.int32, device=qkv.device)
+        work = torch.empty(heads, dtype=torch.int32, device=qkv.device) if DYNAMIC_WORK else None
         s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed, work=work)
         q0 = qkv.data_ptr()
         p0 = 0 if kvp is None else kvp.data_ptr()
@@ -538,7 +541,6 @@ class _WindowAttentionPacked(torch.autograd.Function):
                                        _ptr(dth), _ptr(dtw), _ptr(dtd), _ptr(dtok), _ptr(delta), C.byref(s),
                                        _dtype_code(qkv), impl, _stream(qkv))
         _lib.check(rc, "pwa_attn_bwd")
-        _WindowAttentionPacked.last_delta = delta
         dkvp = None
         if I:
             dkvp = torch.cat([dkvp32[0], dkvp32[1]], dim=-1).to(qkv.dtype)          # [B,I,2C]

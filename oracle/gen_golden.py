@@ -145,9 +145,11 @@ def run_pe_case(ref, seed=5):
 
 
 def run_pair_case(ref, seed=11):
-    """ConsecutiveSwinBlocks with PatchMerging (both merge_last_dim variants)."""
+    """ConsecutiveSwinBlocks with PatchMerging (both merge_last_dim variants, plus an odd-everywhere map whose
+    PatchMerging pads every axis, down.py:24-28): output AND the gradients of x, both prompts and every parameter
+    (incl. merge.norm / merge.reduction, down.py:21-53) for the loss sum(out * go), computed in float64."""
     res = {}
-    for tag, mld, dims in (("mld1", True, (8, 8, 4)), ("mld0", False, (7, 8, 4))):
+    for tag, mld, dims in (("mld1", True, (8, 8, 4)), ("mld0", False, (7, 8, 4)), ("odd1", True, (7, 5, 3))):
         torch.manual_seed(seed)
         pair = ref.ConsecutiveSwinBlocks(hidden_channels=12, num_heads=2, pos_bias_embed_dim=16,
                                          max_prompts=1, tokens_per_prompt=8, window_size=(4, 4, 2),
@@ -159,14 +161,30 @@ def run_pair_case(ref, seed=11):
         for k, v in pair.state_dict().items():
             res[f"{tag}.sd.{k}"] = v.detach().clone().numpy()
         res[f"{tag}.x"], res[f"{tag}.p0"], res[f"{tag}.p1"] = x.numpy(), p0.numpy(), p1.numpy()
-        y = pair.double()(x.double(), (p0.double(), p1.double()))
+        pair64 = pair.double()
+        x64 = x.double().requires_grad_(True)
+        p64 = [p0.double().requires_grad_(True), p1.double().requires_grad_(True)]
+        y = pair64(x64, tuple(p64))
+        go = _rand_like_ref_inputs(g, tuple(y.shape))
+        (y * go.double()).sum().backward()
         res[f"{tag}.out"] = y.detach().float().numpy()
+        res[f"{tag}.go"] = go.numpy()
+        res[f"{tag}.grad.x"] = x64.grad.float().numpy()
+        res[f"{tag}.grad.p0"] = p64[0].grad.float().numpy()
+        res[f"{tag}.grad.p1"] = p64[1].grad.float().numpy()
+        for n, prm in pair64.named_parameters():
+            res[f"{tag}.grad.{n}"] = (prm.grad.float().numpy() if prm.grad is not None
+                                      else np.zeros(prm.shape, np.float32))
     return res
 
 
 def main():
     ref = ref_loader.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "--pair-only" in sys.argv:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "pair_merge.npz"), **run_pair_case(ref))
+        print("wrote pair_merge")
+        return
     for i, case in enumerate(BLOCK_CASES):
         data = run_block_case(ref, case, seed=100 + i)
         np.savez_compressed(os.path.join(GOLDEN_DIR, case[0] + ".npz"), **data)

@@ -8,11 +8,13 @@ N content tokens of a window are used as queries (the reference also runs the I 
 rows as queries and then cuts them, `swin_transformer/swin_block.py:222-225`).
 
 Parity pinning: the reference has no tests/goldens of its own; this file is pinned by
-`tests/golden/*.npz`, produced by `oracle/gen_golden.py` from the live reference, and
-re-checked against the live reference whenever /root/reference is present
-(`tests/test_oracle_vs_reference.py`).
+`tests/golden/*.npz`, produced by `oracle/gen_golden.py` from the live reference
+(`tests/test_oracle_golden.py` holds this file to those vectors).
 
-Everything is plain torch on CPU tensors, differentiable, dtype-agnostic (fp32/fp64).
+Everything is plain torch, differentiable, dtype-agnostic (fp32/fp64) and device-agnostic: the CPU is where
+it is pinned against the goldens; the BASELINE-size parity tests (`tests/test_gpu_multiwindow.py`) let torch
+execute the SAME functions in float64 on the GPU, because a 2.8 GB logit tensor per block takes minutes on
+host cores.  None of the repo's kernels is involved either way.
 """
 from __future__ import annotations
 
@@ -105,7 +107,7 @@ def partition_tokens(x: torch.Tensor, ws, shift, pads) -> torch.Tensor:
     """[B,C,H,W,D] -> [B,P,N,C] (zero where padding)."""
     B, C = x.shape[:2]
     dims = tuple(x.shape[2:])
-    idx = torch.from_numpy(gather_index(dims, ws, shift, pads))
+    idx = torch.from_numpy(gather_index(dims, ws, shift, pads)).to(x.device)
     P, N = idx.shape
     flat = x.reshape(B, C, -1)
     flat = torch.cat([flat, flat.new_zeros(B, C, 1)], dim=2)      # slot -1 -> zeros
@@ -118,7 +120,7 @@ def reverse_tokens(y: torch.Tensor, dims, ws, shift, pads) -> torch.Tensor:
     Uses the CROP offsets, which differ from the data offsets for odd remainders (see
     pad_amounts).  Every output voxel is hit exactly once."""
     B, P, N, C = y.shape
-    idx = torch.from_numpy(gather_index(dims, ws, shift, pads, crop_lo(pads))).reshape(-1)
+    idx = torch.from_numpy(gather_index(dims, ws, shift, pads, crop_lo(pads))).reshape(-1).to(y.device)
     keep = idx >= 0
     src = y.permute(0, 3, 1, 2).reshape(B, C, P * N)[:, :, keep]
     out = y.new_zeros(B, C, dims[0] * dims[1] * dims[2])
@@ -180,8 +182,8 @@ def bias_tables(pe: Dict[str, torch.Tensor], ws, embed_dim: int, num_prompt_toke
         enc = pe[f"enc_content_{name}"]
         wt = pe[f"weights_content_{name}"]
         cap = (enc.shape[0] + 1) // 2
-        i = torch.arange(w).reshape(-1, 1)
-        j = torch.arange(w).reshape(1, -1)
+        i = torch.arange(w, device=enc.device).reshape(-1, 1)
+        j = torch.arange(w, device=enc.device).reshape(1, -1)
         rel = torch.clamp(j - i + cap - 1, 0, 2 * (cap - 1))
         tabs.append(torch.einsum("hc,nmc->hnm", wt, enc[rel]) * (scale / 3.0))
     tok = None
@@ -241,6 +243,32 @@ def dropout_keep_factor(seed_words, B, P, num_heads, N, NK, p_drop):
     return torch.from_numpy(keep.astype(np.float64) * (256.0 / (256 - t))).reshape(B, P, num_heads, N, NK)
 
 
+def dropout_keep_factor_torch(seed_words, bw0, n_bw, num_heads, N, NK, p_drop, device="cpu"):
+    """dropout_keep_factor for the (sample, window) pairs bw0 .. bw0+n_bw-1 only, as torch int64 arithmetic on
+    `device`: float64 [n_bw, h, N, NK].  Same hash, same byte selection (tests/test_host_cpu.py compares the two)."""
+    M = 0xFFFFFFFF
+
+    def mix(x):
+        x = x & M
+        x = x ^ (x >> 16); x = (x * 0x21f0aaad) & M
+        x = x ^ (x >> 15); x = (x * 0x735a2d97) & M
+        x = x ^ (x >> 15)
+        return x
+
+    t = min(int(p_drop * 256.0 + 0.5), 255)
+    if p_drop > 0 and t == 0:
+        t = 1
+    s0, s1 = (int(w) & M for w in seed_words)
+    NH = (N + 1) // 2
+    ar = lambda n, shape: torch.arange(n, dtype=torch.int64, device=device).reshape(shape)
+    bw = ar(n_bw, (-1, 1, 1, 1)) + bw0
+    hd, n, j = ar(num_heads, (1, -1, 1, 1)), ar(N, (1, 1, -1, 1)), ar(NK, (1, 1, 1, -1))
+    rs = mix(s0 + ((((bw * num_heads + hd) * NH + (n >> 1)) * 0x85EBCA77) & M)) ^ s1
+    bits = mix(rs ^ (((j >> 1) * 0x9E3779B1) & M))
+    byte = (bits >> (8 * ((n & 1) * 2 + (j & 1)))) & 0xFF
+    return (byte >= t).to(torch.float64) * (256.0 / (256 - t))
+
+
 def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads, drop=None):
     """q,k,v [B,P,N,C]; kp,vp [B,I,C] or None; bias [h,N,N+I]; ids int [P,N] or None.
     window_attention.py:45-59: logits = (q.k^T*scale + bias) * mask, softmax over keys, [dropout,] @ v.
@@ -262,7 +290,7 @@ def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads, drop
         vh = torch.cat([vh, vph], dim=3)
     s = torch.matmul(qh, kh.transpose(-1, -2)) * scale + bias.to(qh.dtype)[None, None]
     if ids is not None:
-        t = torch.as_tensor(ids)
+        t = torch.as_tensor(ids).to(s.device)
         m = (t[:, :, None] == t[:, None, :]).to(s.dtype)                       # [P,N,N]
         if kp is not None:
             m = torch.cat([m, m.new_ones(P, N, kp.shape[1])], dim=2)

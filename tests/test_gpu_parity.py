@@ -16,6 +16,15 @@ DEV = "cuda:0"
 RTOL_F32 = 1e-4
 RTOL_BF16 = 2e-2
 
+
+def _bf16_param_tol(name, ws):
+    """2e-2 (north_star) everywhere, except the position-bias parameter gradients of the TOY windows (ws 4x4x2, <= 16
+    windows in the batch): those are sums of strongly cancelling dS terms over a few hundred logits, where the bf16
+    rounding of q/k/v/out (2^-9 each) does not average out -- measured 2.0e-2 .. 2.6e-2 against the float64 reference.
+    At BASELINE's window (8x8x4) and stage shapes every gradient is held to 2e-2 (tests/test_gpu_multiwindow.py:
+    measured <= 1.1e-2)."""
+    return 1.5 * RTOL_BF16 if ("pe." in name and tuple(ws) == (4, 4, 2)) else RTOL_BF16
+
 GEOMS = [
     ((16, 16, 16), (8, 8, 4), (4, 4, 2)), ((8, 8, 24), (4, 4, 2), (2, 2, 1)), ((12, 12, 8), (8, 8, 4), (4, 4, 2)),
     ((8, 8, 4), (4, 4, 2), (2, 2, 1)), ((6, 6, 6), (4, 4, 2), (2, 2, 1)), ((6, 8, 4), (4, 4, 2), (2, 2, 1)),
@@ -78,7 +87,11 @@ def test_partition_full_size_round_trip(dims, C, B, dtype):
         assert torch.equal(back, PF._reverse_raw(tok, g, 0, force_word=True))
         assert torch.equal(back, PF._reverse_raw(tok, g, 0, force_vec=True))
         # checksum of checksums: a permutation (+ zero padding) preserves the multiset of values
-        assert torch.equal(tok.float().sum(dim=(1, 2)).sum(), tok.float().sum(dim=(1, 2)).sum())
+        # (float64 sums of the same multiset in a different order agree to round-off; sum of squares guards against
+        #  sign / duplication errors the plain sum could cancel)
+        for f in (lambda t: t.double().sum(), lambda t: t.double().square().sum()):
+            a, b = f(tok).item(), f(x).item()
+            assert abs(a - b) <= 1e-9 * max(1.0, f(x.abs()).item())
         assert tok.count_nonzero() == x.count_nonzero()
         idx = torch.from_numpy(g.index_map_host(0).astype(np.int64)).to(DEV).reshape(-1)
         flat = torch.cat([x.reshape(B, C, -1), x.new_zeros(B, C, 1)], dim=2)
@@ -226,10 +239,10 @@ def test_block_vs_reference_golden_bf16(name):
     y.backward(go.to(DEV, torch.bfloat16))
     assert rel_linf(xd.grad, grads["x"]) < RTOL_BF16
     if p is not None:
-        assert rel_linf(pd.grad, grads["p"]) < 2 * RTOL_BF16        # summed over windows: see DESIGN.md tolerances
+        assert rel_linf(pd.grad, grads["p"]) < RTOL_BF16
     for n, prm in blk.named_parameters():
         g = prm.grad if prm.grad is not None else torch.zeros_like(prm)
-        assert rel_linf(g, grads[n]) < 2 * RTOL_BF16, n
+        assert rel_linf(g, grads[n]) < _bf16_param_tol(n, meta["ws"]), n
 
 
 def test_pair_with_merge_and_checkpoint():
@@ -256,6 +269,32 @@ def test_pair_with_merge_and_checkpoint():
         assert torch.equal(outs[0][0], outs[1][0])
         for a, b in zip(outs[0][1:], outs[1][1:]):
             assert rel_linf(a, b) < 1e-5
+
+
+@pytest.mark.parametrize("tag,mld", [("mld1", True), ("mld0", False), ("odd1", True)])
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, RTOL_F32), (torch.bfloat16, RTOL_BF16)])
+def test_pair_with_merge_all_gradients_vs_reference_golden(tag, mld, dtype, rtol):
+    """ConsecutiveSwinBlocks + PatchMerging (down.py:21-53) forward AND backward against the live reference's float64
+    results: x, both prompts, and every parameter of both blocks and of merge.norm / merge.reduction."""
+    from tests.util import load_npz
+    d = load_npz("pair_merge")
+    sd = {k[len(tag) + 4:]: torch.from_numpy(v) for k, v in d.items() if k.startswith(tag + ".sd.")}
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=12, num_heads=2, pos_bias_embed_dim=16, max_prompts=1,
+                                          tokens_per_prompt=8, window_size=(4, 4, 2), down=True, merge_last_dim=mld)
+    pair.load_state_dict(sd)
+    pair.to(DEV)
+    t = lambda k: torch.from_numpy(d[f"{tag}.{k}"])
+    x = t("x").to(DEV, dtype).requires_grad_(True)
+    p0, p1 = t("p0").to(DEV, dtype).requires_grad_(True), t("p1").to(DEV, dtype).requires_grad_(True)
+    y = pair(x, (p0, p1))
+    assert rel_linf(y, t("out")) < rtol
+    y.backward(t("go").to(DEV, dtype))
+    assert rel_linf(x.grad, t("grad.x")) < rtol
+    assert rel_linf(p0.grad, t("grad.p0")) < rtol
+    assert rel_linf(p1.grad, t("grad.p1")) < rtol
+    for n, prm in pair.named_parameters():
+        g = prm.grad if prm.grad is not None else torch.zeros_like(prm)
+        assert rel_linf(g, t("grad." + n)) < (rtol if dtype == torch.float32 else _bf16_param_tol(n, (4, 4, 2))), n
 
 
 def test_full_size_attention_properties():

@@ -143,3 +143,13 @@ def test_token_split_picks_a_divisor_near_72():
         assert S and T % S == 0 and 32 <= S <= 160, (T, S)
         assert all(abs(d - 72) >= abs(S - 72) for d in range(32, 161) if T % d == 0)
     assert _token_split(1000003) == 0 and _token_split(31) == 0
+
+
+def test_dropout_mask_restatements_agree():
+    """oracle: the numpy and the torch (device-agnostic, chunkable) restatements of the kernels' dropout hash mask."""
+    for words, p_drop in (([123456789, 987654321], 0.25), ([31337, -5], 0.1), ([0, 0], 0.003)):
+        a = R.dropout_keep_factor(words, 2, 3, 4, 6, 10, p_drop)
+        b = R.dropout_keep_factor_torch(words, 0, 6, 4, 6, 10, p_drop).reshape(2, 3, 4, 6, 10)
+        assert torch.equal(a, b)
+        c = R.dropout_keep_factor_torch(words, 3, 3, 4, 6, 10, p_drop)
+        assert torch.equal(a.reshape(6, 4, 6, 10)[3:], c)

@@ -10,8 +10,8 @@ from . import functional
 from . import graphs
 from .graphs import GraphedStep
 from .modules import (ConsecutiveSwinBlocks, SwinTransformerBlock, PatchMerging, WindowAttention, RelativePE,
-                      BiasTables, window_partition, window_reverse, get_attn_mask)
+                      BiasTables, window_partition, window_reverse, get_attn_mask, SwinUnetR, SwinUnetRConfig, SwinUpBlock)
 
 __all__ = ['ConsecutiveSwinBlocks', 'SwinTransformerBlock', 'PatchMerging', 'WindowAttention', 'RelativePE',
            'BiasTables', 'window_partition', 'window_reverse', 'get_attn_mask', 'Geometry', 'get_geometry',
-           'functional', 'graphs', 'GraphedStep']
+           'functional', 'graphs', 'GraphedStep', 'SwinUnetR', 'SwinUnetRConfig', 'SwinUpBlock']

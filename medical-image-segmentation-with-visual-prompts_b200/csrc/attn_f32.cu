@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
   const uint8_t* ids_s = (const uint8_t*)(sm + L.ids);
   const bool masked = p.ids != nullptr;
   const bool drop = p.drop_thresh != 0;
+  const DropThresh dth = drop_thresh_planes(p.drop_thresh);
   const uint32_t seed0 = p.drop_seed ? p.drop_seed[0] : p.seed_host[0], seed1 = p.drop_seed ? p.drop_seed[1] : p.seed_host[1];
 
   for (int i = tid; i < p.NK * DH; i += kThreads) {
@@ -109,8 +110,9 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
     }
     const int id_ = n % p.wd, iw = (n / p.wd) % p.ww, ih = n / (p.wd * p.ww);
     const int rid = masked ? ids_s[n] : 0;
-    const uint32_t rstate = drop ? drop_row_state(seed0, seed1, bw, p.heads, head, (p.N + 1) / 2, n) : 0u;
-    uint32_t dbits = 0;
+    const uint32_t rhash = drop ? drop_row_hash(seed0, seed1, bw, p.heads, head, p.N, n) : 0u;
+    uint32_t kword = 0;
+    int kchunk = -1;
     float m = -1e30f, l = 0.f;
     auto step = [&](int j, float bias, bool keep) {
       float s = bias;
@@ -128,8 +130,11 @@ __global__ void __launch_bounds__(kThreads) attn_fwd_f32_kernel(AttnParams p) {
       float pr = __expf(s - m);
       l += pr;                                            // the softmax denominator is not affected by dropout
       if (drop) {
-        if ((j & 1) == 0 || j == p.N) dbits = drop_block_bits(rstate, (uint32_t)j);
-        if (!drop_keep(dbits, (uint32_t)n, (uint32_t)j, p.drop_thresh)) pr = 0.f;   // (kept ones are scaled once, below)
+        if ((j >> 5) != kchunk) {                         // one keep word per 32 keys (csrc/attn.cuh)
+          kchunk = j >> 5;
+          kword = drop_keep_word(rhash, (uint32_t)kchunk, dth);
+        }
+        if (!drop_keep_elem(kword, (uint32_t)j)) pr = 0.f;   // (kept ones are scaled once, below)
       }
       const float* vr = Vs + j * DH;
 #pragma unroll
@@ -171,6 +176,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
   const uint8_t* ids_s = (const uint8_t*)(sm + L.ids);
   const bool masked = p.ids != nullptr;
   const bool drop = p.drop_thresh != 0;
+  const DropThresh dth = drop_thresh_planes(p.drop_thresh);
   const uint32_t seed0 = p.drop_seed ? p.drop_seed[0] : p.seed_host[0], seed1 = p.drop_seed ? p.drop_seed[1] : p.seed_host[1];
 
   for (int i = tid; i < p.NK * DH; i += kThreads) {
@@ -205,8 +211,9 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
     if (live) p.delta[stat] = delta;
     const int id_ = nn % p.wd, iw = (nn / p.wd) % p.ww, ih = nn / (p.wd * p.ww);
     const int rid = masked ? ids_s[nn] : 0;
-    const uint32_t rstate = drop ? drop_row_state(seed0, seed1, bw, p.heads, head, (p.N + 1) / 2, nn) : 0u;
-    uint32_t dbits = 0;
+    const uint32_t rhash = drop ? drop_row_hash(seed0, seed1, bw, p.heads, head, p.N, nn) : 0u;
+    uint32_t kword = 0;
+    int kchunk = -1;
 
     auto grad = [&](int j, float bias, bool keep) -> float {
       float s = bias;
@@ -220,8 +227,11 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dq_f32_kernel(AttnParams p)
 #pragma unroll
       for (int d = 0; d < DH; ++d) dp = fmaf(dor[d], vr[d], dp);
       if (drop) {   // d P = d P_dropped * mask / keep_rate ; delta = rowsum(dO * O) is unchanged
-        if ((j & 1) == 0 || j == p.N) dbits = drop_block_bits(rstate, (uint32_t)j);
-        dp = drop_keep(dbits, (uint32_t)nn, (uint32_t)j, p.drop_thresh) ? dp * p.inv_keep : 0.f;
+        if ((j >> 5) != kchunk) {
+          kchunk = j >> 5;
+          kword = drop_keep_word(rhash, (uint32_t)kchunk, dth);
+        }
+        dp = drop_keep_elem(kword, (uint32_t)j) ? dp * p.inv_keep : 0.f;
       }
       const float g = keep ? pr * (dp - delta) : 0.f;  // d logits / d (q.k*scale + bias) = mask
 #pragma unroll
@@ -290,6 +300,7 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_f32_kernel(AttnParams p
   const uint8_t* ids_s = (const uint8_t*)(sm + L.ids);
   const bool masked = p.ids != nullptr;
   const bool drop = p.drop_thresh != 0;
+  const DropThresh dth = drop_thresh_planes(p.drop_thresh);
   const uint32_t seed0 = p.drop_seed ? p.drop_seed[0] : p.seed_host[0], seed1 = p.drop_seed ? p.drop_seed[1] : p.seed_host[1];
 
   for (int i = tid; i < p.N * DH; i += kThreads) {
@@ -342,8 +353,10 @@ __global__ void __launch_bounds__(kThreads) attn_bwd_dkv_f32_kernel(AttnParams p
           for (int d = 0; d < DH; ++d) dp = fmaf(dor[d], vr[d], dp);
           float prd = pr;
           if (drop) {
-            if ((n & 1) == 0) dbits = drop_block_bits(drop_row_state(seed0, seed1, bw, p.heads, head, (p.N + 1) / 2, n), (uint32_t)j);
-            const float kf = drop_keep(dbits, (uint32_t)n, (uint32_t)j, p.drop_thresh) ? p.inv_keep : 0.f;
+            // (this kernel walks along queries with one thread per key: a keep word per element -- the fp32-math path
+            //  trades speed for simplicity here; the tcgen05 backward transposes 32x32 bit tiles instead)
+            const uint32_t kword = drop_keep_word(drop_row_hash(seed0, seed1, bw, p.heads, head, p.N, n), (uint32_t)j >> 5, dth);
+            const float kf = drop_keep_elem(kword, (uint32_t)j) ? p.inv_keep : 0.f;
             prd *= kf;
             dp *= kf;
           }

@@ -79,6 +79,31 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 __device__ __forceinline__ int id_slot(uint32_t id) { return id < (uint32_t)(kIds - 1) ? (int)id : kIds - 1; }
+// packed fp32 pairs (sm_100 FFMA2 / FADD2): (d0, d1) = (a0, a1) * b + c ; (s0, s1) += (a0, a1)
+__device__ __forceinline__ void ffma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+  unsigned long long a, bb, cc, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void fadd2(float& s0, float& s1, float a0, float a1) {
+  unsigned long long a, s, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(s) : "f"(s0), "f"(s1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(s), "l"(a));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(d));
+}
+// dropout on the 16 packed pairs of a 32-key chunk: row-sum of the undropped bf16 values, then one AND per pair
+template <int G = 0>
+__device__ __forceinline__ void drop_apply16(uint32_t (&pk)[16], uint32_t kw, float& s0, float& s1) {
+  if constexpr (G < 16) {
+    fadd2(s0, s1, __uint_as_float(pk[G] << 16), __uint_as_float(pk[G] & 0xffff0000u));
+    pk[G] &= drop_pair_mask<G>(kw);
+    drop_apply16<G + 1>(pk, kw, s0, s1);
+  }
+}
 
 template <int DH> struct Cfg {
   static constexpr int DHP = (DH + 1 + 15) / 16 * 16;      // V / O width (PV MMA N) incl. the ones column at DH
@@ -181,7 +206,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
   const float c2 = p.scale * 1.4426950408889634f;          // logits -> log2 domain
   const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
   const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
-  const uint32_t thresh4 = p.drop_thresh * 0x01010101u;
+  const DropThresh dth = drop_thresh_planes(DROP ? p.drop_thresh : 0u);
   const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
 
   // ---- once per CTA: window-independent halves of Q' and K', per-row upper bound of the bias ----
@@ -459,9 +484,8 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
         }
         mb = mx * c2;
       }
-      const uint32_t rstate = DROP ? drop_row_state(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN / 2, (uint32_t)rown) : 0u;
-      const uint32_t rsh = (rown & 1) * 16;                      // this row's two bytes of a block's hash bits
-      float lsum = 0.f;
+      const uint32_t rhash = DROP ? drop_row_hash(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN, (uint32_t)rown) : 0u;
+      float lsum0 = 0.f, lsum1 = 0.f;
       const float e0 = fast_exp2(-mb);                           // weight of every masked (zeroed) logit
       const uint32_t e0pair = pack_bf16(e0, e0);
       const uint32_t* selrow = sel_s + id_slot(rid) * (kN / 4);
@@ -488,7 +512,8 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
           uint32_t pk[16];
 #pragma unroll
           for (int g = 0; g < 16; ++g) {
-            const float x0 = fmaf(__uint_as_float(r[2 * g]), c2, -mb), x1 = fmaf(__uint_as_float(r[2 * g + 1]), c2, -mb);
+            float x0, x1;
+            ffma2(x0, x1, __uint_as_float(r[2 * g]), __uint_as_float(r[2 * g + 1]), c2, -mb);   // one FFMA2 per pair
             const bool poly = (kPolyPairs >> g) & 1u;
             const float p0 = poly ? poly_exp2(x0) : fast_exp2(x0);
             const float p1 = poly ? poly_exp2(x1) : fast_exp2(x1);
@@ -508,13 +533,10 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
             }
           }
           if (DROP) {
-#pragma unroll
-            for (int g = 0; g < 16; ++g) {
-              lsum += __uint_as_float(pk[g] << 16) + __uint_as_float(pk[g] & 0xffff0000u);
-              const uint32_t bits = drop_block_bits(rstate, (uint32_t)(kb * 128 + c * 32 + 2 * g)) >> rsh;
-              // bytes 0 / 1 = keys 2g / 2g+1: per-byte (>= thresh) -> 0xff, spread to the two bf16 halves
-              pk[g] &= __byte_perm(__vcmpgeu4(bits, thresh4), 0u, 0x1100);
-            }
+            // keep bits of this row for the chunk's 32 keys (csrc/attn.cuh); the denominator is summed from the bf16
+            // values the MMA would have consumed without dropout (after the shift mask)
+            const uint32_t kw = drop_keep_word(rhash, (uint32_t)(kb * 4 + c), dth);
+            drop_apply16(pk, kw, lsum0, lsum1);
           }
           tmem_st16(trow + c * 16, pk);
         }
@@ -567,7 +589,7 @@ __global__ void __launch_bounds__(kRows, (DH <= 12 ? 4 : (DH <= 24 ? 2 : 1))) at
       }
 
       // ---- epilogue: normalise, write bf16 output row slice and log-sum-exp ----
-      const float l_run = DROP ? lsum : o_run[DH];
+      const float l_run = DROP ? lsum0 + lsum1 : o_run[DH];
       const float inv = (DROP ? p.inv_keep : 1.f) / l_run;
       __nv_bfloat16* og = (__nv_bfloat16*)p.out + ((size_t)bw * kN + rown) * p.C + head * DH;
       if constexpr (DH % 4 == 0) {

@@ -96,7 +96,7 @@ __host__ __device__ inline BwdSmem bwd_layout(int KS, int DHP, int NKT, int wh, 
   s.lse2 = o; o += kN * 4;
   s.delta = o; o += kN * 4;
   s.wp = o; o += kN * 2;                          // bf16 exp(-lse) per query (value of a masked P entry)
-  s.rs = o; o += (kN / 2) * 4;                    // dropout hash state per query pair (csrc/attn.cuh)
+  s.rs = o; o += kN * 4;                          // dropout hash of every query row (csrc/attn.cuh: drop_row_hash)
   s.sel = o; o += masked ? kIds * (kN / 4) * 4 : 0;   // PRMT selectors [id slot][4 tokens], as in attn_tc.cu
   s.ids = o; o += kN;
   s.opnd_bytes = (o + 127) & ~127u;
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   const float c2 = p.scale * 1.4426950408889634f;
   const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
   const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
-  const uint32_t thresh4 = p.drop_thresh * 0x01010101u;
+  const DropThresh dth = drop_thresh_planes(DROP ? p.drop_thresh : 0u);
   const float keep_scale = DROP ? p.inv_keep : 1.f;
   const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
 
@@ -374,6 +374,15 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
           // ---- this thread: key = lane_row, rows r0 .. r0+31, in two passes of 16 (register budget: 768 threads) ----
           const int r0 = mt * 128 + hf * 64 + wg * 32;
           const uint32_t cid = do_mask ? ids_s[kb * 128 + lane_row] : 0;
+          // dropout: this warp's tile is 32 keys (one key chunk) x 32 rows.  Lane l builds the keep word of row
+          // r0 + drop_bitpos_inv(l), the 32x32 bit tile is transposed across the warp, and every lane fetches the word of
+          // its key's bit position: bit drop_bitpos(i) of T = keep(row r0 + i, this thread's key), the same pair layout
+          // as in the forward kernel, along rows.
+          uint32_t T = 0u;
+          if (DROP) {
+            const uint32_t kwd = drop_keep_word(rs_s[r0 + drop_bitpos_inv(lane)], (uint32_t)(kb * 4 + (warp & 3)), dth);
+            T = __shfl_sync(0xffffffffu, drop_transpose_tile(kwd, lane), drop_bitpos(lane));
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t s[16], dp[16];
@@ -392,27 +401,28 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
                 dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
               }
               float pv[4], gv[4];
-              uint32_t keep[2] = {0xffffffffu, 0xffffffffu};       // per row pair: byte 0 / byte 2 = first / second row
+              uint32_t km[2][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}};   // per row pair: masks of its first / second row, packed pair mask
               if (DROP) {
-                const int rp = (r0 + h * 16 + q4 * 4) >> 1;
-                const uint32_t jb = 8u * ((uint32_t)lane_row & 1u);
-                const uint32_t key = (uint32_t)(kb * 128 + lane_row);
-                keep[0] = __vcmpgeu4(drop_block_bits(rs_s[rp], key) >> jb, thresh4);
-                keep[1] = __vcmpgeu4(drop_block_bits(rs_s[rp + 1], key) >> jb, thresh4);
+                drop_elem_masks(T, h * 8 + q4 * 2, km[0][0], km[0][1], km[0][2]);
+                drop_elem_masks(T, h * 8 + q4 * 2 + 1, km[1][0], km[1][1], km[1][2]);
               }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int r = q4 * 4 + e;
                 pv[e] = fast_exp2(fmaf(__uint_as_float(s[r]), c2, -lv[e]));
-                float dpe = __uint_as_float(dp[r]);
-                if (DROP) dpe = (keep[e >> 1] & ((e & 1) ? 0xff0000u : 0xffu)) ? dpe * keep_scale : 0.f;
-                gv[e] = pv[e] * (FOLD ? dpe : dpe - dv[e]);
+                if (DROP) {                                        // d P = mask * d P~ / keep_rate, then - delta
+                  const float dpe = __uint_as_float(dp[r] & km[e >> 1][e & 1]);
+                  gv[e] = pv[e] * fmaf(dpe, keep_scale, -dv[e]);
+                } else {
+                  const float dpe = __uint_as_float(dp[r]);
+                  gv[e] = pv[e] * (FOLD ? dpe : dpe - dv[e]);
+                }
               }
               pk[q4 * 2] = pack_bf16(pv[0], pv[1]);
               pk[q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
               if (DROP) {                                          // (applied below, after the shift mask)
-                dmask[q4 * 2] = __byte_perm(keep[0], 0u, 0x2200);
-                dmask[q4 * 2 + 1] = __byte_perm(keep[1], 0u, 0x2200);
+                dmask[q4 * 2] = km[0][2];
+                dmask[q4 * 2 + 1] = km[1][2];
               }
               gk[q4 * 2] = pack_bf16(gv[0], gv[1]);
               gk[q4 * 2 + 1] = pack_bf16(gv[2], gv[3]);
@@ -610,8 +620,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
       if (all || part == 0) {
         STAMP(1);
         if (DROP)
-          for (int m = pt; m < kN / 2; m += kProd)
-            rs_s[m] = drop_row_state(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN / 2, (uint32_t)(2 * m));
+          for (int m = pt; m < kN; m += kProd)
+            rs_s[m] = drop_row_hash(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN, (uint32_t)m);
         if (MASKED)
           for (int i = pt; i < kN / 4; i += kProd)
             reinterpret_cast<uint32_t*>(ids_s)[i] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[i];

@@ -403,7 +403,7 @@ def layer_norm_with_passthrough(x, gamma, beta, eps: float = 1e-6):
 
 
 def layer_norm(x, gamma, beta, eps: float = 1e-6):
-    """LayerNorm over the last axis on the pwa kernel (C % 4 == 0, C <= 1024)."""
+    """LayerNorm over the last axis on the pwa kernel (C % 4 == 0, C <= 2048)."""
     _require_cuda(x, gamma, beta)
     return _AddLayerNorm.apply(x, None, gamma, beta, eps)
 
@@ -418,7 +418,7 @@ def add_layer_norm(x, res, gamma, beta, eps: float = 1e-6, bias_of_x=None, bias_
 
 
 def layer_norm_supported(C: int) -> bool:
-    return C % 4 == 0 and C <= 1024
+    return C % 4 == 0 and C <= 2048
 
 
 # ------------------------------------------------------------------------------------------------

@@ -211,41 +211,61 @@ def dense_bias(th, tw, td, tok) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # attention + block
 # --------------------------------------------------------------------------------------
+_DROP_PLANE_MUL = (0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F, 0x165667B1, 0xD3A2646D, 0xFD7046C5, 0xB55A4F09)
+
+
+def _drop_bitpos(jj):
+    """Bit of a 32-key keep word that holds key jj of the chunk (csrc/attn.cuh: drop_bitpos)."""
+    g, odd = jj >> 1, jj & 1
+    return ((31 if odd else 23) if g < 8 else (15 if odd else 7)) - (g & 7)
+
+
+def _drop_threshold(p_drop):
+    t = min(int(p_drop * 256.0 + 0.5), 255)
+    return 1 if (p_drop > 0 and t == 0) else t
+
+
 def dropout_keep_factor(seed_words, B, P, num_heads, N, NK, p_drop):
-    """The attention-dropout mask of the B200 kernels (csrc/attn.cuh: drop_row_state / drop_block_bits / drop_keep),
-    restated with numpy: float64 [B,P,h,N,NK] holding 0 for dropped and 1/keep_rate for kept entries.  The reference
-    applies nn.Dropout to the dense probabilities (window_attention.py:57); the kernels cannot reproduce torch's Philox
-    stream over a tensor they never materialise, so parity is: same distribution (Bernoulli, rate in steps of 1/256,
-    inverse-keep-rate scaling) and exact agreement with THIS mask for given seed words."""
+    """The attention-dropout mask of the B200 kernels (csrc/attn.cuh: drop_row_hash / drop_keep_word), restated with
+    numpy: float64 [B,P,h,N,NK] holding 0 for dropped and 1/keep_rate for kept entries.  The reference applies
+    nn.Dropout to the dense probabilities (window_attention.py:57); the kernels cannot reproduce torch's Philox stream
+    over a tensor they never materialise, so parity is: same distribution (Bernoulli, rate in steps of 1/256,
+    inverse-keep-rate scaling) and exact agreement with THIS mask for given seed words.
+    Per (sample*window, head, query row) one avalanche hash; per 32-key chunk a folded value y; eight planes
+    fold16(y * M_k); key jj of the chunk reads bit drop_bitpos(jj) of every plane, plane k = bit k of an 8-bit number,
+    kept iff number >= round(256 p)."""
     M = np.uint64(0xFFFFFFFF)
+    u = np.uint64
 
     def mix(x):
         x = x & M
-        x ^= x >> np.uint64(16); x = (x * np.uint64(0x21f0aaad)) & M
-        x ^= x >> np.uint64(15); x = (x * np.uint64(0x735a2d97)) & M
-        x ^= x >> np.uint64(15)
+        x ^= x >> u(16); x = (x * u(0x21f0aaad)) & M
+        x ^= x >> u(15); x = (x * u(0x735a2d97)) & M
+        x ^= x >> u(15)
         return x
 
-    t = int(p_drop * 256.0 + 0.5)
-    t = min(t, 255)
-    if p_drop > 0 and t == 0:
-        t = 1
-    s0, s1 = (np.uint64(int(w) & 0xFFFFFFFF) for w in seed_words)
-    NH = (N + 1) // 2
+    t = _drop_threshold(p_drop)
+    s0, s1 = (u(int(w) & 0xFFFFFFFF) for w in seed_words)
     bw = np.arange(B * P, dtype=np.uint64)[:, None, None, None]
     hd = np.arange(num_heads, dtype=np.uint64)[None, :, None, None]
     n = np.arange(N, dtype=np.uint64)[None, None, :, None]
     j = np.arange(NK, dtype=np.uint64)[None, None, None, :]
-    rs = mix(s0 + (((bw * np.uint64(num_heads) + hd) * np.uint64(NH) + (n >> np.uint64(1))) * np.uint64(0x85EBCA77) & M)) ^ s1
-    bits = mix(rs ^ (((j >> np.uint64(1)) * np.uint64(0x9E3779B1)) & M))
-    byte = (bits >> (np.uint64(8) * ((n & np.uint64(1)) * np.uint64(2) + (j & np.uint64(1))))) & np.uint64(0xFF)
-    keep = byte >= np.uint64(t)
+    row = mix(s0 + ((((bw * u(num_heads) + hd) * u(N) + n) * u(0x85EBCA77)) & M)) ^ s1
+    y = ((row ^ (((j >> u(5)) * u(0x9E3779B1)) & M)) * u(0x2C1B3C6D)) & M
+    y ^= y >> u(15)
+    pos = np.array([_drop_bitpos(int(v) & 31) for v in range(NK)], dtype=np.uint64)[None, None, None, :]
+    num = np.zeros(y.shape, dtype=np.uint64)
+    for k, mk in enumerate(_DROP_PLANE_MUL):
+        w = (y * u(mk)) & M
+        w ^= w >> u(16)
+        num |= ((w >> pos) & u(1)) << u(k)
+    keep = num >= u(t)
     return torch.from_numpy(keep.astype(np.float64) * (256.0 / (256 - t))).reshape(B, P, num_heads, N, NK)
 
 
 def dropout_keep_factor_torch(seed_words, bw0, n_bw, num_heads, N, NK, p_drop, device="cpu"):
     """dropout_keep_factor for the (sample, window) pairs bw0 .. bw0+n_bw-1 only, as torch int64 arithmetic on
-    `device`: float64 [n_bw, h, N, NK].  Same hash, same byte selection (tests/test_host_cpu.py compares the two)."""
+    `device`: float64 [n_bw, h, N, NK].  Same hash, same bit selection (tests/test_host_cpu.py compares the two)."""
     M = 0xFFFFFFFF
 
     def mix(x):
@@ -255,18 +275,21 @@ def dropout_keep_factor_torch(seed_words, bw0, n_bw, num_heads, N, NK, p_drop, d
         x = x ^ (x >> 15)
         return x
 
-    t = min(int(p_drop * 256.0 + 0.5), 255)
-    if p_drop > 0 and t == 0:
-        t = 1
+    t = _drop_threshold(p_drop)
     s0, s1 = (int(w) & M for w in seed_words)
-    NH = (N + 1) // 2
     ar = lambda n, shape: torch.arange(n, dtype=torch.int64, device=device).reshape(shape)
     bw = ar(n_bw, (-1, 1, 1, 1)) + bw0
     hd, n, j = ar(num_heads, (1, -1, 1, 1)), ar(N, (1, 1, -1, 1)), ar(NK, (1, 1, 1, -1))
-    rs = mix(s0 + ((((bw * num_heads + hd) * NH + (n >> 1)) * 0x85EBCA77) & M)) ^ s1
-    bits = mix(rs ^ (((j >> 1) * 0x9E3779B1) & M))
-    byte = (bits >> (8 * ((n & 1) * 2 + (j & 1)))) & 0xFF
-    return (byte >= t).to(torch.float64) * (256.0 / (256 - t))
+    row = mix(s0 + ((((bw * num_heads + hd) * N + n) * 0x85EBCA77) & M)) ^ s1
+    y = ((row ^ (((j >> 5) * 0x9E3779B1) & M)) * 0x2C1B3C6D) & M
+    y = y ^ (y >> 15)
+    pos = torch.tensor([_drop_bitpos(v & 31) for v in range(NK)], dtype=torch.int64, device=device).reshape(1, 1, 1, -1)
+    num = torch.zeros_like(y)
+    for k, mk in enumerate(_DROP_PLANE_MUL):
+        w = (y * mk) & M
+        w = w ^ (w >> 16)
+        num = num | (((w >> pos) & 1) << k)
+    return (num >= t).to(torch.float64) * (256.0 / (256 - t))
 
 
 def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads, drop=None):

@@ -193,6 +193,8 @@ enum {
 // the packed pairs, after the shift mask; the inverse keep rate is applied when dV is drained), dP^T is masked and
 // scaled before delta is subtracted (so delta cannot ride in the dP^T MMA: FOLD is off).
 template <int DH, bool MASKED, bool DROP>
+// (72 registers is the hard cap: 25 warps spread 7/6/6/6 over the four sub-partitions of 16 384 registers each, and
+//  7 warps x 32 x 80 does not fit -- a __maxnreg__(80) build fails to launch)
 __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p) {
   constexpr int DHP = BCfg<DH>::DHP, KS = BCfg<DH>::KS, DKC = BCfg<DH>::DKC, NBUF = BCfg<DH>::NBUF;
   constexpr bool FOLD = BCfg<DH>::FOLD && !DROP;

@@ -153,3 +153,20 @@ def test_dropout_mask_restatements_agree():
         assert torch.equal(a, b)
         c = R.dropout_keep_factor_torch(words, 3, 3, 4, 6, 10, p_drop)
         assert torch.equal(a.reshape(6, 4, 6, 10)[3:], c)
+
+
+@pytest.mark.parametrize("name,mode,dec_prompt", [("model_cfg1", 'self_supervised_learning_encoder', False),
+                                                  ("model_cfg3_small", 'self_supervised_learning_all', True),
+                                                  ("model_cfg4_small", 'downstream', True)])
+def test_swin_unetr_state_dict_and_freeze_logic_match_reference(name, mode, dec_prompt):
+    """MONAI-free SwinUnetR host: exactly the reference model's state-dict keys and shapes (reference
+    checkpoints load unchanged; incl. MONAI Convolution's child name `conv`) and the same set of trainable parameters per
+    training mode (swin_unetr.py:21-40), recorded from the live reference by oracle/gen_golden_model.py."""
+    from oracle import gen_golden_model as G
+    d = load_npz(name)
+    model = pwa_b200.SwinUnetR(G.model_conf(mode, dec_prompt=dec_prompt))
+    ours = [f"{k}:{'x'.join(str(v) for v in t.shape)}" for k, t in model.state_dict().items()]
+    assert sorted(ours) == sorted(str(s) for s in d["sd_keys"])
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == [str(s) for s in d["trainable"]]
+    if mode == 'downstream':
+        assert sorted(id(p) for _, p in model.named_parameters_downstream()) == sorted(id(p) for p in model.parameters() if p.requires_grad)

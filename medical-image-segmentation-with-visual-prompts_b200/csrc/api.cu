@@ -84,7 +84,12 @@ extern "C" int pwa_attn_fwd(const void* q, const void* k, const void* v, const v
     set_error("pwa_attn_fwd: tcgen05 kernel does not support this shape/dtype");
     return PWA_ERR_UNSUPPORTED;
   }
-  if (impl == 2 || (impl == 0 && tc_ok)) return attn_tc_forward(p, st);
+  if (impl == 2 || (impl == 0 && tc_ok)) {
+    // PWA_FWD_WS=0 (test infrastructure): the round-1 kernel (four 128-thread CTAs per SM) for A/B measurements
+    static const int use_ws = getenv("PWA_FWD_WS") ? atoi(getenv("PWA_FWD_WS")) : 1;
+    if (use_ws && attn_ws_supported(p, dtype)) return attn_ws_forward(p, st);
+    return attn_tc_forward(p, st);
+  }
   return attn_f32_forward(p, dtype, st);
 }
 

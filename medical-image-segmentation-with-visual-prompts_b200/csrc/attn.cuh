@@ -117,6 +117,8 @@ int attn_f32_backward(const AttnParams& p, int dtype, cudaStream_t st);
 // bf16 tcgen05 / TMEM kernels (attn_tc.cu)
 bool attn_tc_supported(const AttnParams& p, int dtype);
 int attn_tc_forward(const AttnParams& p, cudaStream_t st);
+bool attn_ws_supported(const AttnParams& p, int dtype);       // attn_tc_ws.cu: warp-specialised forward
+int attn_ws_forward(const AttnParams& p, cudaStream_t st);
 bool attn_tc_bwd_supported(const AttnParams& p, int dtype);   // attn_tc_bwd.cu
 int attn_tc_backward(const AttnParams& p, cudaStream_t st);
 

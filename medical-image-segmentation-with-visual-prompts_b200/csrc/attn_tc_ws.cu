@@ -1,0 +1,782 @@
+// (b) fused prompted window attention forward, warp-specialised (tcgen05 + TMEM, bf16 I/O) -- round-2 kernel.
+//
+// One persistent CTA per SM (512 threads) = one fixed head, walking (sample, window) pairs.  The softmax of this path
+// is bound by the MUFU pipe (one ex2 per logit, 16 / clk / SM), so everything else is taken off the threads that
+// compute exponentials and hidden behind them with mbarrier hand-offs:
+//     warps 0-3 / 4-7   softmax group 0 / 1: query tile 0 / 1 (128 rows = 128 TMEM lanes) of the current window.  Per UNIT
+//                       of 64 keys: wait for S, tcgen05.ld -> exp2 (FFMA2 + MUFU + pack) -> shift mask (one PRMT per
+//                       packed pair) -> dropout (one AND per pair) -> tcgen05.st of the bf16 probabilities over the
+//                       consumed S columns; per window: drain O, normalise, write the output rows and the log-sum-exp.
+//     warps 8-11        staging: the NEXT window's Q / K / [V | 1] head slices global -> registers -> UMMA canonical
+//                       shared-memory layouts (double-buffered operand sets), |q|^2 per row and max |k|^2 (stabiliser),
+//                       region ids + PRMT selector table; also fetches the next window index (per-head work counter).
+//     warp 12 / 13      MMA issuer of group 0 / 1 (one lane): S = Q'.K'^T of unit n + 2 is issued while the group still
+//                       works on unit n (three S buffers per group in TMEM), O += P.[V | 1] as soon as a unit's P is
+//                       stored.  A thread's tcgen05.mma instructions execute in issue order, so S(n + 3) may overwrite the
+//                       buffer whose P fed PV(n) without a further barrier.
+// The arithmetic is that of attn_tc.cu (round 1): no row-max pass (norm-bound stabiliser with an exact-max sweep as the
+// rare fallback), no online rescaling, relative-position bias folded into the QK^T MMA through one-hot / table columns,
+// multiplicative pre-softmax shift mask (window_attention.py:49-58), ones column of V for the softmax denominator,
+// bit-sliced dropout keep words (csrc/attn.cuh).  TMEM: per group 3 x 64 columns of S / P plus 1-2 O accumulators.
+#include "attn.cuh"
+#include "tc_common.cuh"
+
+namespace pwa {
+using namespace tc;
+
+namespace {
+
+constexpr int kN = 256;           // content tokens per window
+constexpr int kIds = 28;          // region ids 0..26 and 100 (-> 27)
+// Warp roles.  The softmax warps get the HIGHEST warp ids: the scheduler favours high ids among eligible warps, and the
+// staging warps' bursts of packing / store instructions otherwise delay the MUFU issue of the softmax warps.
+constexpr int kThreadsW = 448;    // 14 warps
+constexpr int kStage0 = 0;        // staging warps 0-3
+constexpr int kIssue0 = 4;        // issuer warps 4 (group 0) and 5 (group 1)
+constexpr int kSoft0 = 6;         // softmax group 0 = warps 6-9, group 1 = warps 10-13 (any four consecutive warps cover the
+                                  // four TMEM lane quadrants warp % 4)
+constexpr int kStageThreads = 128;
+constexpr int kUK = 64;           // keys per unit
+constexpr int kNSB = 3;           // S / P buffers per group
+constexpr float kMaxBoundW = 40.f;
+
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// volatile: keeps the 32 exponentials of a chunk back to back in program order.  Left to itself ptxas pairs every pack
+// with the two MUFUs just in front of it, and the pack then waits out the MUFU latency 16 times per chunk (ncu: the F2FP
+// lines carried as many stall samples as the MUFU lines).
+__device__ __forceinline__ float ex2f_v(float x) {
+  float y;
+  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t prmt3(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ int id_slot_w(uint32_t id) { return id < (uint32_t)(kIds - 1) ? (int)id : kIds - 1; }
+__device__ __forceinline__ void ffma2w(float& d0, float& d1, float a0, float a1, float b, float c) {
+  unsigned long long a, bb, cc, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void fadd2w(float& s0, float& s1, float a0, float a1) {
+  unsigned long long a, s, d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(s) : "f"(s0), "f"(s1));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(s), "l"(a));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(d));
+}
+template <int G = 0>
+__device__ __forceinline__ void drop_apply16w(uint32_t (&pk)[16], uint32_t kw, float& s0, float& s1) {
+  if constexpr (G < 16) {
+    fadd2w(s0, s1, __uint_as_float(pk[G] << 16), __uint_as_float(pk[G] & 0xffff0000u));
+    pk[G] &= drop_pair_mask<G>(kw);
+    drop_apply16w<G + 1>(pk, kw, s0, s1);
+  }
+}
+
+template <int DH> struct WCfg {
+  static constexpr int DHP = (DH + 1 + 15) / 16 * 16;      // V / O width (PV MMA N) incl. the ones column at DH
+  static constexpr int NDC = DHP / 8;
+  static constexpr int KS = (DH + 4 + 15) / 16;            // k-steps of the staged [q | onehot_d] operand
+  static constexpr int NOB = DHP <= 32 ? 2 : 1;            // O accumulators per group
+  static constexpr int GC = kNSB * kUK + NOB * DHP;        // TMEM columns per group
+  static_assert(2 * GC <= 512, "TMEM column budget");
+};
+
+struct WsHeader {
+  int bw;          // (sample * P + window) of this operand set, -1 = no more work
+  int exact;       // 1: some row's stabiliser bound is loose -> exact row-max sweep first
+  float kmax;      // max |k| over the window's keys (content + prompt) of this head
+  int next_bw;
+};
+
+struct WsSmem {
+  uint32_t qaug, kaug, rowb;                                // shared by all windows
+  uint32_t q, k, v, sel, ids, qn2, hdr, opnd_bytes;         // per operand buffer
+  uint32_t opnd0;
+  int opb;
+  uint32_t total;
+};
+
+__host__ __device__ inline WsSmem ws_layout(int KS, int DHP, int NKT, bool masked) {
+  WsSmem s;
+  uint32_t o = 0;
+  s.q = o; o += KS * 2 * kN * 16;
+  s.k = o; o += KS * 2 * NKT * 16;
+  s.v = o; o += NKT * DHP * 2;
+  s.sel = o; o += masked ? kIds * (kN / 4) * 4 : 0;
+  s.ids = o; o += kN;
+  s.qn2 = o; o += kN * 4;
+  s.hdr = o; o += 32;
+  s.opnd_bytes = (o + 127) & ~127u;
+  uint32_t sh = 0;
+  s.qaug = sh; sh += 2 * kN * 16;
+  s.kaug = sh; sh += 2 * NKT * 16;
+  s.rowb = sh; sh += kN * 4;
+  sh = (sh + 127) & ~127u;
+  s.opnd0 = sh;
+  s.opb = (sh + 2 * s.opnd_bytes <= 200u * 1024u) ? 2 : 1;
+  s.total = sh + s.opb * s.opnd_bytes;
+  return s;
+}
+
+template <int DH>
+__device__ __forceinline__ void load_row_w(const __nv_bfloat16* src, __nv_bfloat16 (&dst)[DH]) {
+  if constexpr (DH % 4 == 0) {
+    const uint2* s2 = reinterpret_cast<const uint2*>(src);
+    uint2* d2 = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+    for (int i = 0; i < DH / 4; ++i) d2[i] = __ldg(s2 + i);
+  } else {
+#pragma unroll
+    for (int i = 0; i < DH; ++i) dst[i] = src[i];
+  }
+}
+template <int DH>
+__device__ __forceinline__ float sumsq_w(const __nv_bfloat16 (&r)[DH]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < DH; ++i) {
+    const float v = __bfloat162float(r[i]);
+    s = fmaf(v, v, s);
+  }
+  return s;
+}
+// staged K-dim layout of one head: [real DH | up to 4 extra columns | zero pad] -> KS k-steps of 16
+template <int DH, int KS>
+__device__ __forceinline__ void store_chunks_w(uint8_t* base, uint32_t chunk_stride, int row, const __nv_bfloat16 (&real)[DH],
+                                               const __nv_bfloat16 (&extra)[4], int n_extra) {
+#pragma unroll
+  for (int c = 0; c < KS * 2; ++c) {
+    __align__(16) __nv_bfloat16 tmp[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int col = c * 8 + e;
+      const int x = col - DH;
+      __nv_bfloat16 v = __float2bfloat16(0.f);
+      if (col < DH) v = real[col < DH ? col : 0];
+      else if (x < 4 && x < n_extra) v = extra[x & 3];
+      tmp[e] = v;
+    }
+    *reinterpret_cast<uint4*>(base + c * chunk_stride + row * 16) = *reinterpret_cast<const uint4*>(tmp);
+  }
+}
+
+__device__ __forceinline__ void stage_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kStageThreads) : "memory"); }
+
+// cycle accounting of CTA 0 (make TIMELINE=1, PWA_TIMELINE=1 in the environment; tools/ws_profile.py): every role adds
+// the clocks it spends per phase to private counters and writes them out at the end of the kernel
+#ifdef PWA_TIMELINE_BUILD
+#define WS_PROF_DECL(n) long long prof_[n] = {}; long long prof_t_ = clock64()
+#define WS_PROF(i) do { const long long t_ = clock64(); prof_[i] += t_ - prof_t_; prof_t_ = t_; } while (0)
+#define WS_PROF_OUT(base, n) do { if (p.debug && p.delta && blockIdx.x == 0) { long long* o_ = reinterpret_cast<long long*>(p.delta) + (base); for (int i_ = 0; i_ < (n); ++i_) o_[i_] = prof_[i_]; } } while (0)
+#else
+#define WS_PROF_DECL(n) do { } while (0)
+#define WS_PROF(i) do { } while (0)
+#define WS_PROF_OUT(base, n) do { } while (0)
+#endif
+
+enum { bOpFull = 0, bOpFree = 2, bSFull = 4, bPReady = 10, bOFull = 16, bOFree = 20, kNumBarsW = 24 };
+
+template <int DH, bool MASKED, bool DROP>
+__global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p) {
+  constexpr int DHP = WCfg<DH>::DHP, NDC = WCfg<DH>::NDC, KS = WCfg<DH>::KS, NOB = WCfg<DH>::NOB, GC = WCfg<DH>::GC;
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar[kNumBarsW];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t kmax_w[2][4];
+  __shared__ float tab_s[16 * 16 + 4 * 4 + 128 + 4];            // th | tw (wh + ww <= 16) | td (wd <= 4) | tok (I <= 128) | max tok
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int NKT = kN + p.I;
+  const WsSmem L = ws_layout(KS, DHP, NKT, MASKED);
+  const int OPB = L.opb;
+  uint8_t* Qa = smem + L.qaug;
+  uint8_t* Ka = smem + L.kaug;
+  float* rowb_s = reinterpret_cast<float*>(smem + L.rowb);
+  const int head = blockIdx.x % p.heads;
+  const float inv_scale = 1.f / p.scale;
+  const float c2 = p.scale * 1.4426950408889634f;          // logits -> log2 domain
+  const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
+  const int n_units = (NKT + kUK - 1) / kUK;
+  const int last_nk = NKT - kUK * (n_units - 1);            // 64 or 32
+  const int n_pairs = p.B * p.P;
+  const int stride = gridDim.x / p.heads;
+
+  // ---- once per CTA: bias tables of this head -> smem, window-independent halves of Q' and K', per-row bias bound ----
+  float* th_s = tab_s;
+  float* tw_s = th_s + p.wh * p.wh;
+  float* td_s = tw_s + p.ww * p.ww;
+  float* tok_s = td_s + p.wd * p.wd;
+  for (int i = tid; i < p.wh * p.wh; i += kThreadsW) th_s[i] = p.th[head * p.wh * p.wh + i];
+  for (int i = tid; i < p.ww * p.ww; i += kThreadsW) tw_s[i] = p.tw[head * p.ww * p.ww + i];
+  for (int i = tid; i < p.wd * p.wd; i += kThreadsW) td_s[i] = p.td[head * p.wd * p.wd + i];
+  for (int i = tid; i < p.I; i += kThreadsW) tok_s[i] = p.tok[head * p.I + i];
+  __syncthreads();
+  if (warp == 0) {
+    float bt = -1e30f;
+    for (int j = lane; j < p.I; j += 32) bt = fmaxf(bt, tok_s[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bt = fmaxf(bt, __shfl_xor_sync(0xffffffffu, bt, o));
+    if (lane == 0) tok_s[p.I] = bt;
+  }
+  __syncthreads();
+  for (int n = tid; n < kN; n += kThreadsW) {
+    const int id_ = n % p.wd, iw = (n / p.wd) % p.ww, ih = n / (p.wd * p.ww);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      __align__(16) __nv_bfloat16 tmp[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int col = c * 8 + e;
+        tmp[e] = (col < p.wh) ? (col == ih ? one : zero) : ((col - p.wh < p.ww && col - p.wh == iw) ? one : zero);
+      }
+      *reinterpret_cast<uint4*>(Qa + c * (kN * 16) + n * 16) = *reinterpret_cast<const uint4*>(tmp);
+    }
+    float bh = -1e30f, bw_ = -1e30f, bd = -1e30f;
+    const float bt = tok_s[p.I];
+    for (int j = 0; j < p.wh; ++j) bh = fmaxf(bh, th_s[ih * p.wh + j]);
+    for (int j = 0; j < p.ww; ++j) bw_ = fmaxf(bw_, tw_s[iw * p.ww + j]);
+    for (int j = 0; j < p.wd; ++j) bd = fmaxf(bd, td_s[id_ * p.wd + j]);
+    rowb_s[n] = (p.I > 0 ? fmaxf(bh + bw_ + bd, bt) : bh + bw_ + bd) * inv_scale;   // max_j bias[n][j] / scale
+  }
+  for (int j = tid; j < NKT; j += kThreadsW) {
+    const bool content = j < kN;
+    const int jw = (j / p.wd) % p.ww, jh = j / (p.wd * p.ww);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      __align__(16) __nv_bfloat16 tmp[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int col = c * 8 + e;
+        float v = 0.f;
+        if (content) {
+          if (col < p.wh) v = th_s[col * p.wh + jh];
+          else if (col - p.wh < p.ww) v = tw_s[(col - p.wh) * p.ww + jw];
+        } else if (col < p.wh) {
+          v = tok_s[j - kN];
+        }
+        tmp[e] = __float2bfloat16(v * inv_scale);
+      }
+      *reinterpret_cast<uint4*>(Ka + c * (NKT * 16) + j * 16) = *reinterpret_cast<const uint4*>(tmp);
+    }
+  }
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar[bOpFull + i], kStageThreads);
+      mbar_init(&bar[bOpFree + i], 256);
+    }
+    for (int i = 0; i < 6; ++i) {
+      mbar_init(&bar[bSFull + i], 1);
+      mbar_init(&bar[bPReady + i], 128);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&bar[bOFull + i], 1);
+      mbar_init(&bar[bOFree + i], 128);
+    }
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp >= kSoft0) {
+    // =============================================================================================
+    // softmax groups
+    // =============================================================================================
+    const int g = (warp - kSoft0) >> 2;
+    const int tg = (warp & 3) * 32 + lane;                          // row within the tile = TMEM lane
+    const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * GC);
+    const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
+    const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
+    const DropThresh dth = drop_thresh_planes(DROP ? p.drop_thresh : 0u);
+    uint32_t ucount = 0, tcount = 0;
+    WS_PROF_DECL(8);          // 0 wait operands, 1 window setup, 2 wait S, 3 exp pass, 4 st + arrive, 5 wait O, 6 epilogue
+    for (int it = 0;; ++it) {
+      const int ob = it % OPB;
+      uint8_t* opnd = smem + L.opnd0 + ob * L.opnd_bytes;
+      WS_PROF(6);
+      mbar_wait(&bar[bOpFull + ob], (it / OPB) & 1);
+      WS_PROF(0);
+      const WsHeader* hdr = reinterpret_cast<const WsHeader*>(opnd + L.hdr);
+      const int bw = hdr->bw;
+      if (bw < 0) break;
+      const bool exact = hdr->exact != 0;
+      const uint32_t* sel_s = reinterpret_cast<const uint32_t*>(opnd + L.sel);
+      const uint8_t* ids_s = opnd + L.ids;
+      const int rown = g * 128 + tg;
+      const uint32_t rid = MASKED ? ids_s[rown] : 0;
+      float mb;
+      {
+        const float qk = sqrtf(reinterpret_cast<const float*>(opnd + L.qn2)[rown]) * hdr->kmax, rb = rowb_s[rown];
+        mb = c2 * 1.01f * (qk + fmaxf(rb, 0.f));
+      }
+      if (exact) {
+        // rare path: exact row maximum of the masked logits (masked entries count as 0, as in the reference); the issuer
+        // runs the S MMAs of every unit once more for the real pass
+        float mx = -1e30f;
+        for (int u = 0; u < n_units; ++u) {
+          const uint32_t buf = ucount % kNSB;
+          mbar_wait(&bar[bSFull + g * kNSB + buf], (ucount / kNSB) & 1);
+          tc_fence_after();
+          const int nk = u == n_units - 1 ? last_nk : kUK;
+          const bool do_mask = MASKED && u * kUK < kN;
+          for (int c = 0; c < nk / 32; ++c) {
+            uint32_t r[32];
+            tmem_ld32(trow + buf * kUK + c * 32, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              float s = __uint_as_float(r[e]);
+              if (do_mask && ids_s[u * kUK + c * 32 + e] != rid) s = 0.f;
+              mx = fmaxf(mx, s);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&bar[bPReady + g * kNSB + buf]);
+          ++ucount;
+        }
+        mb = mx * c2;
+      }
+      const uint32_t rhash = DROP ? drop_row_hash(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN, (uint32_t)rown) : 0u;
+      float lsum0 = 0.f, lsum1 = 0.f;
+      const float e0 = ex2f(-mb);                                  // weight of every masked (zeroed) logit
+      const uint32_t e0pair = pack_bf16(e0, e0);
+      const uint32_t* selrow = sel_s + id_slot_w(rid) * (kN / 4);
+      WS_PROF(1);
+
+      // The window's chunks of 32 keys form one stream k = 0 .. n_chunks-1 (unit u = k >> 1, chunk c = k & 1); the
+      // tcgen05.ld of chunk k + 1 is in flight while chunk k is exponentiated (two register sets, loop unrolled by two).
+      const int n_chunks = 2 * (n_units - 1) + last_nk / 32;
+      const uint32_t u0 = ucount;                                  // unit counter at the window's first unit
+      auto load_chunk = [&](int k, uint32_t (&dst)[32]) {
+        const uint32_t un = u0 + (uint32_t)(k >> 1), buf = un % kNSB;
+        if ((k & 1) == 0) {                                        // first chunk of a unit: its S must be complete
+          mbar_wait(&bar[bSFull + g * kNSB + buf], (un / kNSB) & 1);
+          tc_fence_after();
+        }
+        tmem_ld32(trow + buf * kUK + (k & 1) * 32, dst);
+      };
+      auto process_chunk = [&](int k, const uint32_t (&r)[32]) {
+        const int u = k >> 1, c = k & 1;
+        const uint32_t buf = (u0 + (uint32_t)u) % kNSB;
+        const bool do_mask = MASKED && u * kUK < kN;
+        uint32_t pk[16];
+        float x[32];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) ffma2w(x[2 * q], x[2 * q + 1], __uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), c2, -mb);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = ex2f_v(x[q]);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) pk[q] = pack_bf16(x[2 * q], x[2 * q + 1]);
+        if (do_mask) {
+          const uint4* sp = reinterpret_cast<const uint4*>(selrow + u * (kUK / 4) + c * 8);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const uint4 s4 = sp[h];
+            const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+              pk[h * 8 + w * 2] = prmt3(pk[h * 8 + w * 2], e0pair, sw[w]);
+              pk[h * 8 + w * 2 + 1] = prmt3(pk[h * 8 + w * 2 + 1], e0pair, sw[w] >> 16);
+            }
+          }
+        }
+        if (DROP) {
+          const uint32_t kw = drop_keep_word(rhash, (uint32_t)k, dth);
+          drop_apply16w(pk, kw, lsum0, lsum1);
+        }
+        tmem_st16(trow + buf * kUK + c * 16, pk);
+        if (c == 1 || k == n_chunks - 1) {                         // last chunk of its unit: hand P to the issuer
+          tmem_wait_st();
+          tc_fence_before();
+          mbar_arrive(&bar[bPReady + g * kNSB + buf]);
+        }
+      };
+      {
+        uint32_t ra[32], rb[32];
+        load_chunk(0, ra);
+        for (int k = 0; k < n_chunks; k += 2) {
+          tmem_wait_ld();
+          if (k + 1 < n_chunks) load_chunk(k + 1, rb);
+          process_chunk(k, ra);
+          if (k + 1 < n_chunks) {
+            tmem_wait_ld();
+            if (k + 2 < n_chunks) load_chunk(k + 2, ra);
+            process_chunk(k + 1, rb);
+          }
+        }
+        ucount += (uint32_t)n_units;
+        WS_PROF(3);
+      }
+
+      // ---- O of this tile: drain, normalise, write the bf16 output row slice and the log-sum-exp ----
+      const uint32_t obuf = tcount % NOB;
+      mbar_wait(&bar[bOFull + g * 2 + obuf], (tcount / NOB) & 1);
+      tc_fence_after();
+      WS_PROF(5);
+      float o_run[DHP];
+#pragma unroll
+      for (int dq = 0; dq < DHP / 16; ++dq) {
+        uint32_t o[16];
+        tmem_ld16(trow + kNSB * kUK + obuf * DHP + dq * 16, o);
+        tmem_wait_ld();
+#pragma unroll
+        for (int d = 0; d < 16; ++d) o_run[dq * 16 + d] = __uint_as_float(o[d]);
+      }
+      tc_fence_before();
+      mbar_arrive(&bar[bOFree + g * 2 + obuf]);
+      ++tcount;
+      const float l_run = DROP ? lsum0 + lsum1 : o_run[DH];
+      const float inv = (DROP ? p.inv_keep : 1.f) / l_run;
+      __nv_bfloat16* og = (__nv_bfloat16*)p.out + ((size_t)bw * kN + rown) * p.C + head * DH;
+      if constexpr (DH % 4 == 0) {
+#pragma unroll
+        for (int d = 0; d < DH; d += 4) {
+          uint2 v;
+          v.x = pack_bf16(o_run[d] * inv, o_run[d + 1] * inv);
+          v.y = pack_bf16(o_run[d + 2] * inv, o_run[d + 3] * inv);
+          *reinterpret_cast<uint2*>(og + d) = v;
+        }
+      } else {
+#pragma unroll
+        for (int d = 0; d < DH; ++d) og[d] = __float2bfloat16(o_run[d] * inv);
+      }
+      p.lse[((size_t)bw * p.heads + head) * kN + rown] = (mb + __log2f(l_run)) * 0.6931471805599453f;
+      mbar_arrive(&bar[bOpFree + ob]);                              // this thread is done with the operand set
+    }
+    WS_PROF(6);
+    if (tid == kSoft0 * 32) WS_PROF_OUT(0, 8);
+    if (tid == (kSoft0 + 4) * 32) WS_PROF_OUT(8, 8);
+  } else if (warp < kStage0 + 4) {
+    // =============================================================================================
+    // staging warps: operand set of window `it` into buffer it % OPB
+    // =============================================================================================
+    const int st = tid - kStage0 * 32;
+    const int sw = warp - kStage0;
+    int bw = blockIdx.x / p.heads;
+    WS_PROF_DECL(8);          // 0 wait free, 1 loads + layout stores, 2 barrier, 3 selectors + bound, 4 windows
+    for (int it = 0;; ++it) {
+      const int ob = it % OPB;
+      uint8_t* opnd = smem + L.opnd0 + ob * L.opnd_bytes;
+      uint8_t* Qs = opnd + L.q;
+      uint8_t* Ks = opnd + L.k;
+      uint8_t* Vs = opnd + L.v;
+      uint32_t* sel_s = reinterpret_cast<uint32_t*>(opnd + L.sel);
+      uint8_t* ids_s = opnd + L.ids;
+      float* qn2_s = reinterpret_cast<float*>(opnd + L.qn2);
+      WsHeader* hdr = reinterpret_cast<WsHeader*>(opnd + L.hdr);
+      WS_PROF(3);
+      if (it >= OPB) mbar_wait(&bar[bOpFree + ob], ((it / OPB) - 1) & 1);
+      WS_PROF(0);
+      const bool stop = bw >= n_pairs;
+      if (st == 0) {
+        hdr->bw = stop ? -1 : bw;
+        hdr->exact = 0;
+        // the window after this one: static for the first, then from this head's counter (CTAs do not progress evenly)
+        hdr->next_bw = stop ? bw : (p.work ? stride + (int)atomicAdd(p.work + head, 1u) : bw + stride);
+      }
+      float qn2[2] = {0.f, 0.f};
+      float kmax2 = 0.f;
+      if (!stop) {
+        const int b = bw / p.P, win = bw - b * p.P;
+        auto kv_off = [&](int j) {
+          return j < kN ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
+        };
+        auto stage_q = [&](int t, const __nv_bfloat16 (&row)[DH]) {
+          const int n = t * 128 + st;
+          qn2[t] = sumsq_w<DH>(row);
+          qn2_s[n] = qn2[t];
+          const int id_ = n % p.wd;
+          __nv_bfloat16 extra[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
+          store_chunks_w<DH, KS>(Qs, kN * 16, n, row, extra, p.wd);
+        };
+        auto stage_k = [&](int j, const __nv_bfloat16 (&row)[DH]) {
+          const bool content = j < kN;
+          kmax2 = fmaxf(kmax2, sumsq_w<DH>(row));
+          const int jd = j % p.wd;
+          __nv_bfloat16 extra[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            extra[u] = (content && u < p.wd) ? __float2bfloat16(td_s[u * p.wd + jd] * inv_scale) : zero;
+          store_chunks_w<DH, KS>(Ks, NKT * 16, j, row, extra, p.wd);
+        };
+        auto stage_v = [&](int j, const __nv_bfloat16 (&row)[DH]) {
+#pragma unroll
+          for (int dc = 0; dc < NDC; ++dc) {
+            __align__(16) __nv_bfloat16 tmp[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              tmp[e] = (dc * 8 + e < DH) ? row[dc * 8 + e < DH ? dc * 8 + e : 0] : (dc * 8 + e == DH ? one : zero);
+            *reinterpret_cast<uint4*>(Vs + (j >> 3) * (NDC * 128) + dc * 128 + (j & 7) * 16) = *reinterpret_cast<const uint4*>(tmp);
+          }
+        };
+        if (MASKED && st < kN / 4)
+          reinterpret_cast<uint32_t*>(ids_s)[st] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[st];
+        if constexpr (DH <= 12) {
+          // every global load of this thread in flight before the first use (the round trips are what staging costs)
+          constexpr int KR = 3;                                      // key rows per thread: NKT <= 384 (I <= 128)
+          __nv_bfloat16 qrow[2][DH], krow[KR][DH], vrow[KR][DH];
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            load_row_w<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + t * 128 + st) * p.ldq + head * DH, qrow[t]);
+#pragma unroll
+          for (int i = 0; i < KR; ++i) {
+            const int j = i * 128 + st;
+            if (j < NKT) {
+              load_row_w<DH>((const __nv_bfloat16*)(j < kN ? p.k : p.kp) + kv_off(j), krow[i]);
+              load_row_w<DH>((const __nv_bfloat16*)(j < kN ? p.v : p.vp) + kv_off(j), vrow[i]);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < 2; ++t) stage_q(t, qrow[t]);
+#pragma unroll
+          for (int i = 0; i < KR; ++i) {
+            const int j = i * 128 + st;
+            if (j < NKT) {
+              stage_k(j, krow[i]);
+              stage_v(j, vrow[i]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            __nv_bfloat16 row[DH];
+            load_row_w<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + t * 128 + st) * p.ldq + head * DH, row);
+            stage_q(t, row);
+          }
+          for (int j = st; j < NKT; j += 128) {
+            __nv_bfloat16 row[DH], vrow[DH];
+            load_row_w<DH>((const __nv_bfloat16*)(j < kN ? p.k : p.kp) + kv_off(j), row);
+            load_row_w<DH>((const __nv_bfloat16*)(j < kN ? p.v : p.vp) + kv_off(j), vrow);
+            stage_k(j, row);
+            stage_v(j, vrow);
+          }
+        }
+        kmax2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(kmax2)));   // non-negative floats order as uints
+        if (lane == 0) kmax_w[ob][sw] = __float_as_uint(kmax2);
+      }
+      WS_PROF(1);
+      stage_sync();                                               // ids, kmax partials, header of this operand set
+      WS_PROF(2);
+      const int next_bw = hdr->next_bw;
+      if (!stop) {
+        if (MASKED) {
+          // PRMT selectors: word w of row-id slot s covers keys 4w..4w+3 = packed pairs 2w (low half) and 2w+1 (high
+          // half); a kept bf16 takes its own bytes (nibbles 1,0 / 3,2), a masked one those of the (e0,e0) operand
+          for (int i = st; i < kIds * (kN / 4); i += kStageThreads) {
+            const int s = i / (kN / 4), w = i - s * (kN / 4);
+            const uint32_t idw = reinterpret_cast<const uint32_t*>(ids_s)[w];
+            uint32_t sel = 0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const bool keep = id_slot_w((idw >> (8 * e)) & 0xffu) == s;
+              const uint32_t nib = (e & 1) ? (keep ? 0x32u : 0x76u) : (keep ? 0x10u : 0x54u);
+              sel |= nib << (((e & 1) ? 8 : 0) + ((e >> 1) ? 16 : 0));
+            }
+            sel_s[i] = sel;
+          }
+        }
+        const float kmax = sqrtf(__uint_as_float(max(max(kmax_w[ob][0], kmax_w[ob][1]), max(kmax_w[ob][2], kmax_w[ob][3]))));
+        if (st == 0) hdr->kmax = kmax;
+        // stabiliser: upper bound of the row's logits; the row maximum is >= max_j bias - |q| max|k|, so the gap bounds how
+        // far below the stabiliser the largest exponent argument can lie.  Too loose -> exact-max sweep for this window.
+        bool loose = false;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+          const float qk = sqrtf(qn2[t]) * kmax, rb = rowb_s[t * 128 + st];
+          const float mbt = c2 * 1.01f * (qk + fmaxf(rb, 0.f));
+          loose |= (mbt - c2 * (rb - qk)) > 2.f * kMaxBoundW;
+        }
+        if (loose) atomicOr(&hdr->exact, 1);
+      }
+      fence_proxy_async_smem();
+      mbar_arrive(&bar[bOpFull + ob]);
+      if (stop) break;
+      bw = next_bw;
+#ifdef PWA_TIMELINE_BUILD
+      prof_[4] += 1;
+#endif
+    }
+    WS_PROF(3);
+    if (st == 0) WS_PROF_OUT(16, 8);
+  } else if (warp < kIssue0 + 2) {
+    // =============================================================================================
+    // MMA issuer of group g: S runs two units ahead of PV; tcgen05.mma executes in issue order per thread
+    // =============================================================================================
+    // The WHOLE warp runs the control flow with warp-uniform values (everything read from shared memory goes through a
+    // shuffle broadcast), and only the tcgen05 instructions themselves sit under elect.sync: the MMA operands then live in
+    // uniform registers.  With the loop inside `if (lane == 0)` every MMA was wrapped in an ELECT + 7 x R2UR.BROADCAST
+    // waterfall loop and one thread issued an MMA only every ~170 clk -- the issuer was the kernel's critical path.
+    {
+      const int g = __shfl_sync(0xffffffffu, warp - kIssue0, 0);
+      const uint32_t tg = __shfl_sync(0xffffffffu, tmem, 0) + (uint32_t)(g * GC);
+      const uint32_t idescS64 = make_idesc_bf16(128, 64, 0, 0), idescS32 = make_idesc_bf16(128, 32, 0, 0);
+      const uint32_t idescPV = make_idesc_bf16(128, DHP, 0, 1);
+      struct Cur {
+        int it, pass, u, npass;
+        bool stop, need_open;
+        uint32_t opnd;
+      };
+      auto open_window = [&](Cur& c) {
+        const int ob = c.it % OPB;
+        mbar_wait(&bar[bOpFull + ob], (c.it / OPB) & 1);
+        const WsHeader* hdr = reinterpret_cast<const WsHeader*>(smem + L.opnd0 + ob * L.opnd_bytes + L.hdr);
+        c.stop = __shfl_sync(0xffffffffu, hdr->bw, 0) < 0;
+        c.npass = __shfl_sync(0xffffffffu, hdr->exact, 0) ? 2 : 1;
+        c.pass = 0;
+        c.u = 0;
+        c.need_open = false;
+        c.opnd = smem_u32(smem + L.opnd0 + ob * L.opnd_bytes);
+      };
+      auto advance = [&](Cur& c) {
+        if (++c.u == n_units) {
+          c.u = 0;
+          if (++c.pass == c.npass) {
+            ++c.it;
+            c.need_open = true;
+          }
+        }
+      };
+      Cur cs = {0, 0, 0, 1, false, true, 0u};
+      open_window(cs);
+      Cur cp = cs;
+      uint32_t ns = 0, np = 0, tcount = 0, obuf = 0;
+      WS_PROF_DECL(8);        // 0 issue S (+ operand waits), 1 wait P, 2 wait O free, 3 issue PV
+      for (;;) {
+        // ---- S of up to two units ahead ----
+        while (!cs.stop && ns < np + 2) {
+          if (cs.need_open) {
+            // with ONE operand buffer the next window is staged only after this one has retired completely: all of its
+            // PVs must be issued before this thread may block on the next operand set
+            if (OPB == 1 && np < ns) break;
+            open_window(cs);
+            if (cs.stop) break;
+          }
+          const uint32_t buf = ns % kNSB;
+          const int nk = cs.u == n_units - 1 ? last_nk : kUK;
+          const uint32_t idesc = nk == kUK ? idescS64 : idescS32;
+          const uint32_t koff = (uint32_t)(cs.u * kUK) * 16;
+          tc_fence_after();
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int ks = 0; ks < KS; ++ks) {
+              const uint64_t da = make_smem_desc(cs.opnd + L.q + ks * 2 * (kN * 16) + g * (128 * 16), kN * 16, 128);
+              const uint64_t db = make_smem_desc(cs.opnd + L.k + ks * 2 * (NKT * 16) + koff, NKT * 16, 128);
+              mma_ss(tg + buf * kUK, da, db, idesc, ks > 0);
+            }
+            {
+              const uint64_t da = make_smem_desc(smem_u32(Qa) + g * (128 * 16), kN * 16, 128);
+              const uint64_t db = make_smem_desc(smem_u32(Ka) + koff, NKT * 16, 128);
+              mma_ss(tg + buf * kUK, da, db, idesc, 1);
+            }
+            mma_commit(&bar[bSFull + g * kNSB + buf]);
+          }
+          __syncwarp();
+          ++ns;
+          advance(cs);
+        }
+        if (np == ns) {
+          if (cs.stop) break;                                       // everything issued and consumed
+          continue;                                                 // (OPB == 1: the next window can be opened now)
+        }
+        // ---- PV of unit np ----
+        if (cp.need_open) open_window(cp);
+        const uint32_t buf = np % kNSB;
+        WS_PROF(0);
+        mbar_wait(&bar[bPReady + g * kNSB + buf], (np / kNSB) & 1);
+        tc_fence_after();
+        WS_PROF(1);
+        const bool maxpass = cp.npass == 2 && cp.pass == 0;
+        if (!maxpass) {
+          if (cp.u == 0) {
+            obuf = tcount % NOB;
+            if (tcount >= (uint32_t)NOB) {                          // the accumulator's previous tile has been drained
+              mbar_wait(&bar[bOFree + g * 2 + obuf], ((tcount / NOB) - 1) & 1);
+              tc_fence_after();
+            }
+            WS_PROF(2);
+          }
+          const int nk = cp.u == n_units - 1 ? last_nk : kUK;
+          if (elect_one_sync()) {
+#pragma unroll
+            for (int t = 0; t < kUK / 16; ++t) {
+              if (t * 16 < nk) {
+                const uint64_t dv = make_smem_desc(cp.opnd + L.v + ((cp.u * kUK + t * 16) >> 3) * (NDC * 128), NDC * 128, 128);
+                mma_ts(tg + kNSB * kUK + obuf * DHP, tg + buf * kUK + t * 8, dv, idescPV, (cp.u > 0) | (t > 0));
+              }
+            }
+            if (cp.u == n_units - 1) mma_commit(&bar[bOFull + g * 2 + obuf]);
+          }
+          __syncwarp();
+          if (cp.u == n_units - 1) ++tcount;
+        }
+        ++np;
+        advance(cp);
+        WS_PROF(3);
+      }
+      if (g == 0 && lane == 0) WS_PROF_OUT(24, 8);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+template <int DH>
+int launch_ws(const AttnParams& p, cudaStream_t st) {
+  constexpr int DHP = WCfg<DH>::DHP, KS = WCfg<DH>::KS;
+  const int NKT = kN + p.I;
+  const WsSmem L = ws_layout(KS, DHP, NKT, p.ids != nullptr);
+  const size_t smem = L.total;
+  int grid = 148;
+  grid -= grid % p.heads;
+  if (grid < p.heads) grid = p.heads;
+  const int need = p.B * p.P * p.heads;
+  if (grid > need) grid = need;
+  auto kern = p.drop_thresh ? (p.ids ? attn_fwd_ws_kernel<DH, true, true> : attn_fwd_ws_kernel<DH, false, true>)
+                            : (p.ids ? attn_fwd_ws_kernel<DH, true, false> : attn_fwd_ws_kernel<DH, false, false>);
+  PWA_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (p.work) PWA_CUDA_OK(cudaMemsetAsync(p.work, 0, sizeof(unsigned int) * p.heads, st));
+  kern<<<grid, kThreadsW, smem, st>>>(p);
+  PWA_CUDA_OK(cudaGetLastError());
+  return PWA_OK;
+}
+
+}  // namespace
+
+bool attn_ws_supported(const AttnParams& p, int dtype) {
+  if (!attn_tc_supported(p, dtype)) return false;
+  const int dh = p.C / p.heads;
+  const WsSmem L = ws_layout((dh + 4 + 15) / 16, (dh + 1 + 15) / 16 * 16, kN + p.I, true);
+  return L.total <= 224u * 1024u;
+}
+
+int attn_ws_forward(const AttnParams& p, cudaStream_t st) {
+  switch (p.C / p.heads) {
+    case 3: return launch_ws<3>(p, st);
+    case 6: return launch_ws<6>(p, st);
+    case 12: return launch_ws<12>(p, st);
+    case 24: return launch_ws<24>(p, st);
+    case 48: return launch_ws<48>(p, st);
+  }
+  set_error("tcgen05 attention: head_dim %d not instantiated", p.C / p.heads);
+  return PWA_ERR_UNSUPPORTED;
+}
+
+}  // namespace pwa

@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--batch", type=int, default=4)
     ap.add_argument("--stages", default="enc0,enc1,enc2,dec0")
+    ap.add_argument("--dropout", type=float, default=0.0)
     args = ap.parse_args()
     dev = torch.device("cuda")
     B, I = args.batch, 64
@@ -56,13 +57,16 @@ def main():
                 tok = 0.3 * torch.randn(heads, I, device=dev)
                 ids = g.region_ids(dev) if g.masked else None
                 scale = (C // heads) ** -0.5
-                out = PF.prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads, WS, scale, PF.IMPL_TC)
+                seed = torch.tensor([1234, 5678], dtype=torch.int32, device=dev) if args.dropout > 0 else None
+                out = PF.prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads, WS, scale, PF.IMPL_TC,
+                                                          p_drop=args.dropout, seed=seed)
                 go = torch.randn_like(out)
-                fwd = lambda: PF.prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads, WS, scale, PF.IMPL_TC)
+                fwd = lambda: PF.prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads, WS, scale, PF.IMPL_TC,
+                                                                  p_drop=args.dropout, seed=seed)
                 t_f = timeit(lambda: fwd(), args.iters)
                 t_fb = timeit(lambda: fwd().backward(go), args.iters)
                 fl = 4.0 * B * P * N * (N + I) * C
-                print(json.dumps({"kernel": "attn", "stage": name, "shifted": shifted, "B": B, "P": P, "fwd_us": round(t_f, 1),
+                print(json.dumps({"kernel": "attn", "stage": name, "shifted": shifted, "B": B, "P": P, "drop": args.dropout, "fwd_us": round(t_f, 1),
                                   "bwd_us": round(t_fb - t_f, 1), "fwd_tflops": round(fl / t_f / 1e6, 1),
                                   "bwd_tflops": round(2 * fl / max(t_fb - t_f, 1e-3) / 1e6, 1),
                                   "fwd_Gexp_s": round(B * P * heads * N * (N + I) / t_f / 1e3, 1)}))

@@ -65,6 +65,10 @@ int pwa_geometry(const int32_t dims[3], const int32_t ws[3], const int32_t shift
  * ids are 9*rh+3*rw+rd (0..26) or 100 inside the un-padded box when the map is padded. */
 int pwa_region_ids(const pwa_geom* g, uint8_t* ids_host);
 
+/* PRMT selector table of the shift mask for the tcgen05 attention kernels: uint32 [P][28][N/4] to HOST memory, from
+ * region ids uint8 [P][N] in HOST memory (see pwa_attn_shape.sel_table).  Depends only on the geometry. */
+int pwa_attn_sel_table(const uint8_t* ids_host, int P, int N, uint32_t* table_host);
+
 /* flat source index (into the unpadded H*W*D volume, -1 = zero padding) of every (window, token):
  * int32 [P][N] to HOST memory.  which = 0: input side (pad -> roll -> window_partition,
  * swin_block.py:163,174-178,292-299); which = 1: output side (window_reverse -> roll back -> crop,
@@ -124,6 +128,9 @@ typedef struct pwa_attn_shape {
   const void* seed_dev;        /* optional DEVICE pointer to two uint32 seed words that replace seed/offset: the
                                   words can be refreshed by a device-side RNG op every step, which keeps a captured
                                   CUDA graph of the step valid (host scalars would be frozen into the graph)      */
+  const void* sel_table;       /* optional DEVICE pointer to pwa_attn_sel_table() output [P][28][N/4] uint32 for `ids` (tcgen05
+                                  forward only): fetched per window with one bulk copy instead of being rebuilt by every
+                                  (window, head).  NULL = built in the kernel.                                         */
   void* work;                  /* optional DEVICE scratch of >= 4*heads bytes (contents irrelevant, zeroed by the call on
                                   its stream): per-head work counters of the tcgen05 forward, which then hands windows
                                   to its CTAs dynamically instead of round-robin (CTAs sharing an SM do not progress

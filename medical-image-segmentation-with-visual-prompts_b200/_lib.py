@@ -27,7 +27,7 @@ class PwaAttnShape(C.Structure):
         ("B", C.c_int32), ("P", C.c_int32), ("C", C.c_int32), ("heads", C.c_int32), ("I", C.c_int32),
         ("ws", C.c_int32 * 3), ("scale", C.c_float), ("p_drop", C.c_float),
         ("seed", C.c_uint64), ("offset", C.c_uint64), ("ld_qkv", C.c_int32), ("ld_p", C.c_int32),
-        ("seed_dev", C.c_void_p), ("work", C.c_void_p),
+        ("seed_dev", C.c_void_p), ("sel_table", C.c_void_p), ("work", C.c_void_p),
     ]
 
 
@@ -49,6 +49,8 @@ def _load():
     lib.pwa_geometry.argtypes = [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), gp]
     lib.pwa_region_ids.argtypes = [gp, vp]
     lib.pwa_index_map.argtypes = [gp, i32, vp]
+    lib.pwa_attn_sel_table.argtypes = [vp, i32, i32, vp]
+    lib.pwa_attn_sel_table.restype = i32
     lib.pwa_partition.argtypes = [vp, vp, i32, i32, gp, i32, i32, vp]
     lib.pwa_reverse.argtypes = [vp, vp, i32, i32, gp, i32, i32, vp]
     lib.pwa_reverse_add.argtypes = [vp, vp, vp, i32, i32, gp, i32, i32, vp]
@@ -79,7 +81,7 @@ def _load():
 
 lib = _load()
 
-EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map",
+EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map", "pwa_attn_sel_table",
                     "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
                     "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_debug_fwd_timeline", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 

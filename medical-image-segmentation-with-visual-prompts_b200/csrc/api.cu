@@ -24,6 +24,7 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
     p.inv_keep = 256.f / (float)(256 - t);
     p.drop_seed = (const uint32_t*)s->seed_dev;
     p.work = (unsigned int*)s->work;
+    p.sel = (const uint32_t*)s->sel_table;
     p.seed_host[0] = (uint32_t)(s->seed ^ (s->offset << 32)) ^ (uint32_t)(s->offset >> 7);
     p.seed_host[1] = (uint32_t)(s->seed >> 32) ^ (uint32_t)s->offset * 0x9E3779B1u;
   }

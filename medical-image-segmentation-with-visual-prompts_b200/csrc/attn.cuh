@@ -23,6 +23,7 @@ struct AttnParams {
   float inv_keep;
   const uint32_t* drop_seed;   // DEVICE pointer to two 32-bit seed words (graph-replay safe), or null
   uint32_t seed_host[2];       // used when drop_seed is null
+  const uint32_t* sel;         // forward: optional precomputed PRMT selector table [P][28][N/4] (pwa_attn_sel_table), or null
   unsigned int* work;          // forward: per-head window counters (zeroed by the launcher), or null = static round-robin
   int debug;         // PWA_TIMELINE=1: CTA 0 writes clock64 stamps into the (otherwise unused) delta buffer
 };

@@ -28,13 +28,15 @@ namespace {
 
 constexpr int kN = 256;           // content tokens per window
 constexpr int kIds = 28;          // region ids 0..26 and 100 (-> 27)
-// Warp roles.  The softmax warps get the HIGHEST warp ids: the scheduler favours high ids among eligible warps, and the
-// staging warps' bursts of packing / store instructions otherwise delay the MUFU issue of the softmax warps.
-constexpr int kThreadsW = 448;    // 14 warps
-constexpr int kStage0 = 0;        // staging warps 0-3
-constexpr int kIssue0 = 4;        // issuer warps 4 (group 0) and 5 (group 1)
-constexpr int kSoft0 = 6;         // softmax group 0 = warps 6-9, group 1 = warps 10-13 (any four consecutive warps cover the
-                                  // four TMEM lane quadrants warp % 4)
+// Warp roles (the scheduler favours high warp ids among eligible warps).
+constexpr int kThreadsW = 768;    // 24 warps = 6 per scheduler
+constexpr int kStage0 = 20;       // staging warps 20-23: the HIGHEST ids -- they are few, on the critical path of every window,
+                                  // and must not wait for issue slots behind sixteen always-eligible softmax warps
+constexpr int kIssue0 = 16;       // issuer warps 16 (group 0) and 17 (group 1); warps 18, 19 idle
+constexpr int kSoft0 = 0;         // softmax warps 0-15: group = warp / 8, set = (warp / 4) % 2, TMEM lane quadrant
+                                  // = warp % 4.  The two SETS of a group take alternate units of the group's unit stream, so
+                                  // that four softmax warps per scheduler feed the MUFU pipe (one warp issues an ex2 only
+                                  // every ~8 clk; measured 16 / 21 / 25 results per clk and SM with 1 / 2 / 4 warps each)
 constexpr int kStageThreads = 128;
 constexpr int kUK = 64;           // keys per unit
 constexpr int kNSB = 3;           // S / P buffers per group
@@ -101,7 +103,7 @@ struct WsHeader {
 
 struct WsSmem {
   uint32_t qaug, kaug, rowb;                                // shared by all windows
-  uint32_t q, k, v, sel, ids, qn2, hdr, opnd_bytes;         // per operand buffer
+  uint32_t q, k, v, sel, ids, qn2, hdr, part, opnd_bytes;   // per operand buffer
   uint32_t opnd0;
   int opb;
   uint32_t total;
@@ -117,6 +119,7 @@ __host__ __device__ inline WsSmem ws_layout(int KS, int DHP, int NKT, bool maske
   s.ids = o; o += kN;
   s.qn2 = o; o += kN * 4;
   s.hdr = o; o += 32;
+  s.part = o; o += 2 * kN * 4;                              // per (set, query row): partial softmax denominator / row maximum
   s.opnd_bytes = (o + 127) & ~127u;
   uint32_t sh = 0;
   s.qaug = sh; sh += 2 * kN * 16;
@@ -124,7 +127,7 @@ __host__ __device__ inline WsSmem ws_layout(int KS, int DHP, int NKT, bool maske
   s.rowb = sh; sh += kN * 4;
   sh = (sh + 127) & ~127u;
   s.opnd0 = sh;
-  s.opb = (sh + 2 * s.opnd_bytes <= 200u * 1024u) ? 2 : 1;
+  s.opb = (sh + 3 * s.opnd_bytes <= 200u * 1024u) ? 3 : ((sh + 2 * s.opnd_bytes <= 200u * 1024u) ? 2 : 1);
   s.total = sh + s.opb * s.opnd_bytes;
   return s;
 }
@@ -185,7 +188,9 @@ __device__ __forceinline__ void stage_sync() { asm volatile("bar.sync 1, %0;" ::
 #define WS_PROF_OUT(base, n) do { } while (0)
 #endif
 
-enum { bOpFull = 0, bOpFree = 2, bSFull = 4, bPReady = 10, bOFull = 16, bOFree = 20, kNumBarsW = 24 };
+// bSFull: 6 per group, indexed by unit % 6 -- a set waits only for its own (every second) unit, and with one barrier per
+// S buffer it would skip a phase between two waits, which a parity wait cannot tell apart; unit % 6 is always the same set
+enum { bOpFull = 0, bOpFree = 3, bSFull = 6, bPReady = 18, bOFull = 24, bOFree = 28, bLsum = 32, kNumBarsW = 38 };
 
 template <int DH, bool MASKED, bool DROP>
 __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p) {
@@ -193,7 +198,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar[kNumBarsW];
   __shared__ uint32_t tmem_base_s;
-  __shared__ uint32_t kmax_w[2][4];
+  __shared__ uint32_t kmax_w[3][4];
   __shared__ float tab_s[16 * 16 + 4 * 4 + 128 + 4];            // th | tw (wh + ww <= 16) | td (wd <= 4) | tok (I <= 128) | max tok
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -271,14 +276,14 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
     }
   }
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 3; ++i) {
       mbar_init(&bar[bOpFull + i], kStageThreads);
-      mbar_init(&bar[bOpFree + i], 256);
+      mbar_init(&bar[bOpFree + i], 512);
+      mbar_init(&bar[bLsum + 2 * i], 256);
+      mbar_init(&bar[bLsum + 2 * i + 1], 256);
     }
-    for (int i = 0; i < 6; ++i) {
-      mbar_init(&bar[bSFull + i], 1);
-      mbar_init(&bar[bPReady + i], 128);
-    }
+    for (int i = 0; i < 12; ++i) mbar_init(&bar[bSFull + i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bar[bPReady + i], 128);
     for (int i = 0; i < 4; ++i) {
       mbar_init(&bar[bOFull + i], 1);
       mbar_init(&bar[bOFree + i], 128);
@@ -293,18 +298,19 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (warp >= kSoft0) {
+  if (warp < kSoft0 + 16) {
     // =============================================================================================
-    // softmax groups
+    // softmax warps: group g (query tile g of the window), set (alternate units of the group's stream)
     // =============================================================================================
-    const int g = (warp - kSoft0) >> 2;
+    const int g = (warp - kSoft0) >> 3;
+    const uint32_t set = (uint32_t)((warp - kSoft0) >> 2) & 1u;
     const int tg = (warp & 3) * 32 + lane;                          // row within the tile = TMEM lane
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * GC);
     const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
     const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
     const DropThresh dth = drop_thresh_planes(DROP ? p.drop_thresh : 0u);
-    uint32_t ucount = 0, tcount = 0;
-    WS_PROF_DECL(8);          // 0 wait operands, 1 window setup, 2 wait S, 3 exp pass, 4 st + arrive, 5 wait O, 6 epilogue
+    uint32_t ucount = 0, tcount = 0;                                // units / tiles of this GROUP so far (both sets count all)
+    WS_PROF_DECL(8);          // 0 wait operands, 1 window setup, 3 unit loop, 5 wait O, 6 epilogue
     for (int it = 0;; ++it) {
       const int ob = it % OPB;
       uint8_t* opnd = smem + L.opnd0 + ob * L.opnd_bytes;
@@ -317,6 +323,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
       const bool exact = hdr->exact != 0;
       const uint32_t* sel_s = reinterpret_cast<const uint32_t*>(opnd + L.sel);
       const uint8_t* ids_s = opnd + L.ids;
+      float* part_s = reinterpret_cast<float*>(opnd + L.part);     // [set][query row of the window]
       const int rown = g * 128 + tg;
       const uint32_t rid = MASKED ? ids_s[rown] : 0;
       float mb;
@@ -326,11 +333,13 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
       }
       if (exact) {
         // rare path: exact row maximum of the masked logits (masked entries count as 0, as in the reference); the issuer
-        // runs the S MMAs of every unit once more for the real pass
+        // runs the S MMAs of every unit once more for the real pass.  Each set sees its own units: the two partial maxima
+        // meet in shared memory (named barrier over the group's 256 threads).
         float mx = -1e30f;
-        for (int u = 0; u < n_units; ++u) {
-          const uint32_t buf = ucount % kNSB;
-          mbar_wait(&bar[bSFull + g * kNSB + buf], (ucount / kNSB) & 1);
+        for (int u = 0; u < n_units; ++u, ++ucount) {
+          if ((ucount & 1u) != set) continue;
+          const uint32_t buf = ucount % kNSB, sb = ucount % 6u;
+          mbar_wait(&bar[bSFull + g * 6 + sb], (ucount / 6u) & 1);
           tc_fence_after();
           const int nk = u == n_units - 1 ? last_nk : kUK;
           const bool do_mask = MASKED && u * kUK < kN;
@@ -347,8 +356,11 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
           }
           tc_fence_before();
           mbar_arrive(&bar[bPReady + g * kNSB + buf]);
-          ++ucount;
         }
+        part_s[set * kN + rown] = mx;
+        asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");
+        mx = fmaxf(mx, part_s[(set ^ 1u) * kN + rown]);
+        asm volatile("bar.sync %0, 256;" ::"r"(2 + g) : "memory");  // both partials read before the denominators reuse the slots
         mb = mx * c2;
       }
       const uint32_t rhash = DROP ? drop_row_hash(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN, (uint32_t)rown) : 0u;
@@ -358,115 +370,132 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
       const uint32_t* selrow = sel_s + id_slot_w(rid) * (kN / 4);
       WS_PROF(1);
 
-      // The window's chunks of 32 keys form one stream k = 0 .. n_chunks-1 (unit u = k >> 1, chunk c = k & 1); the
-      // tcgen05.ld of chunk k + 1 is in flight while chunk k is exponentiated (two register sets, loop unrolled by two).
-      const int n_chunks = 2 * (n_units - 1) + last_nk / 32;
-      const uint32_t u0 = ucount;                                  // unit counter at the window's first unit
-      auto load_chunk = [&](int k, uint32_t (&dst)[32]) {
-        const uint32_t un = u0 + (uint32_t)(k >> 1), buf = un % kNSB;
-        if ((k & 1) == 0) {                                        // first chunk of a unit: its S must be complete
-          mbar_wait(&bar[bSFull + g * kNSB + buf], (un / kNSB) & 1);
-          tc_fence_after();
-        }
-        tmem_ld32(trow + buf * kUK + (k & 1) * 32, dst);
-      };
-      auto process_chunk = [&](int k, const uint32_t (&r)[32]) {
-        const int u = k >> 1, c = k & 1;
-        const uint32_t buf = (u0 + (uint32_t)u) % kNSB;
+      bool last_mine = false;                                       // this set handled the window's last unit -> epilogue
+      for (int u = 0; u < n_units; ++u, ++ucount) {
+        if ((ucount & 1u) != set) continue;
+        last_mine = u == n_units - 1;
+        const uint32_t buf = ucount % kNSB, sb = ucount % 6u;
+        mbar_wait(&bar[bSFull + g * 6 + sb], (ucount / 6u) & 1);
+        tc_fence_after();
+        const int nk = u == n_units - 1 ? last_nk : kUK;
         const bool do_mask = MASKED && u * kUK < kN;
-        uint32_t pk[16];
-        float x[32];
+        for (int c = 0; c < nk / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(trow + buf * kUK + c * 32, r);
+          tmem_wait_ld();
+          uint32_t pk[16];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) ffma2w(x[2 * q], x[2 * q + 1], __uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), c2, -mb);
+          for (int q = 0; q < 16; ++q) {
+            float x0, x1;
+            ffma2w(x0, x1, __uint_as_float(r[2 * q]), __uint_as_float(r[2 * q + 1]), c2, -mb);
+            pk[q] = pack_bf16(ex2f(x0), ex2f(x1));
+          }
+          if (do_mask) {
+            const uint4* sp = reinterpret_cast<const uint4*>(selrow + u * (kUK / 4) + c * 8);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) x[q] = ex2f_v(x[q]);
+            for (int h = 0; h < 2; ++h) {
+              const uint4 s4 = sp[h];
+              const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-        for (int q = 0; q < 16; ++q) pk[q] = pack_bf16(x[2 * q], x[2 * q + 1]);
-        if (do_mask) {
-          const uint4* sp = reinterpret_cast<const uint4*>(selrow + u * (kUK / 4) + c * 8);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const uint4 s4 = sp[h];
-            const uint32_t sw[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              pk[h * 8 + w * 2] = prmt3(pk[h * 8 + w * 2], e0pair, sw[w]);
-              pk[h * 8 + w * 2 + 1] = prmt3(pk[h * 8 + w * 2 + 1], e0pair, sw[w] >> 16);
+              for (int w = 0; w < 4; ++w) {
+                pk[h * 8 + w * 2] = prmt3(pk[h * 8 + w * 2], e0pair, sw[w]);
+                pk[h * 8 + w * 2 + 1] = prmt3(pk[h * 8 + w * 2 + 1], e0pair, sw[w] >> 16);
+              }
             }
           }
-        }
-        if (DROP) {
-          const uint32_t kw = drop_keep_word(rhash, (uint32_t)k, dth);
-          drop_apply16w(pk, kw, lsum0, lsum1);
-        }
-        tmem_st16(trow + buf * kUK + c * 16, pk);
-        if (c == 1 || k == n_chunks - 1) {                         // last chunk of its unit: hand P to the issuer
-          tmem_wait_st();
-          tc_fence_before();
-          mbar_arrive(&bar[bPReady + g * kNSB + buf]);
-        }
-      };
-      {
-        uint32_t ra[32], rb[32];
-        load_chunk(0, ra);
-        for (int k = 0; k < n_chunks; k += 2) {
-          tmem_wait_ld();
-          if (k + 1 < n_chunks) load_chunk(k + 1, rb);
-          process_chunk(k, ra);
-          if (k + 1 < n_chunks) {
-            tmem_wait_ld();
-            if (k + 2 < n_chunks) load_chunk(k + 2, ra);
-            process_chunk(k + 1, rb);
+          if (DROP) {
+            const uint32_t kw = drop_keep_word(rhash, (uint32_t)(u * (kUK / 32) + c), dth);
+            drop_apply16w(pk, kw, lsum0, lsum1);
           }
+          tmem_st16(trow + buf * kUK + c * 16, pk);
         }
-        ucount += (uint32_t)n_units;
-        WS_PROF(3);
+        tmem_wait_st();
+        tc_fence_before();
+        mbar_arrive(&bar[bPReady + g * kNSB + buf]);
       }
-
-      // ---- O of this tile: drain, normalise, write the bf16 output row slice and the log-sum-exp ----
-      const uint32_t obuf = tcount % NOB;
-      mbar_wait(&bar[bOFull + g * 2 + obuf], (tcount / NOB) & 1);
-      tc_fence_after();
-      WS_PROF(5);
-      float o_run[DHP];
-#pragma unroll
-      for (int dq = 0; dq < DHP / 16; ++dq) {
-        uint32_t o[16];
-        tmem_ld16(trow + kNSB * kUK + obuf * DHP + dq * 16, o);
-        tmem_wait_ld();
-#pragma unroll
-        for (int d = 0; d < 16; ++d) o_run[dq * 16 + d] = __uint_as_float(o[d]);
+      WS_PROF(3);
+      if (DROP) {                                                   // the two sets' shares of the softmax denominator
+        part_s[set * kN + rown] = lsum0 + lsum1;
+        mbar_arrive(&bar[bLsum + ob * 2 + g]);
       }
-      tc_fence_before();
-      mbar_arrive(&bar[bOFree + g * 2 + obuf]);
+      if (last_mine) {
+        // ---- O of this tile: drain, normalise, write the bf16 output row slice and the log-sum-exp ----
+        const uint32_t obuf = tcount % NOB;
+        mbar_wait(&bar[bOFull + g * 2 + obuf], (tcount / NOB) & 1);
+        tc_fence_after();
+        WS_PROF(5);
+        float o_run[DHP];
+#pragma unroll
+        for (int dq = 0; dq < DHP / 16; ++dq) {
+          uint32_t o[16];
+          tmem_ld16(trow + kNSB * kUK + obuf * DHP + dq * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int d = 0; d < 16; ++d) o_run[dq * 16 + d] = __uint_as_float(o[d]);
+        }
+        tc_fence_before();
+        mbar_arrive(&bar[bOFree + g * 2 + obuf]);
+        float l_run = o_run[DH];
+        if (DROP) {
+          mbar_wait(&bar[bLsum + ob * 2 + g], (it / OPB) & 1);
+          l_run = part_s[rown] + part_s[kN + rown];
+        }
+        const float inv = (DROP ? p.inv_keep : 1.f) / l_run;
+        __nv_bfloat16* og = (__nv_bfloat16*)p.out + ((size_t)bw * kN + rown) * p.C + head * DH;
+        if constexpr (DH % 4 == 0) {
+#pragma unroll
+          for (int d = 0; d < DH; d += 4) {
+            uint2 v;
+            v.x = pack_bf16(o_run[d] * inv, o_run[d + 1] * inv);
+            v.y = pack_bf16(o_run[d + 2] * inv, o_run[d + 3] * inv);
+            *reinterpret_cast<uint2*>(og + d) = v;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < DH; ++d) og[d] = __float2bfloat16(o_run[d] * inv);
+        }
+        p.lse[((size_t)bw * p.heads + head) * kN + rown] = (mb + __log2f(l_run)) * 0.6931471805599453f;
+      }
       ++tcount;
-      const float l_run = DROP ? lsum0 + lsum1 : o_run[DH];
-      const float inv = (DROP ? p.inv_keep : 1.f) / l_run;
-      __nv_bfloat16* og = (__nv_bfloat16*)p.out + ((size_t)bw * kN + rown) * p.C + head * DH;
-      if constexpr (DH % 4 == 0) {
-#pragma unroll
-        for (int d = 0; d < DH; d += 4) {
-          uint2 v;
-          v.x = pack_bf16(o_run[d] * inv, o_run[d + 1] * inv);
-          v.y = pack_bf16(o_run[d + 2] * inv, o_run[d + 3] * inv);
-          *reinterpret_cast<uint2*>(og + d) = v;
-        }
-      } else {
-#pragma unroll
-        for (int d = 0; d < DH; ++d) og[d] = __float2bfloat16(o_run[d] * inv);
-      }
-      p.lse[((size_t)bw * p.heads + head) * kN + rown] = (mb + __log2f(l_run)) * 0.6931471805599453f;
       mbar_arrive(&bar[bOpFree + ob]);                              // this thread is done with the operand set
     }
     WS_PROF(6);
     if (tid == kSoft0 * 32) WS_PROF_OUT(0, 8);
     if (tid == (kSoft0 + 4) * 32) WS_PROF_OUT(8, 8);
-  } else if (warp < kStage0 + 4) {
+  } else if (warp >= kStage0) {
     // =============================================================================================
     // staging warps: operand set of window `it` into buffer it % OPB
     // =============================================================================================
+    // A (window, head) slice is 896 rows of DH bf16 at a row pitch of 3C elements.  One thread per ROW made every load
+    // instruction touch 32 different 128-byte lines (L1 wavefronts, not DRAM, bound the staging: ~6 K clk per window, the
+    // critical path of the whole kernel).  Here consecutive lanes take consecutive 8-byte PIECES of a row, so a warp-wide
+    // load touches ~11 lines, and every piece goes straight to its place in the canonical layouts with one 8-byte store.
+    // The columns beyond DH (one-hot / bias-table columns of Q' and K', the ones column of V, zero padding) do not depend
+    // on the window: they are written once per operand buffer.  |q|^2 and max |k|^2 are computed from shared memory.
     const int st = tid - kStage0 * 32;
     const int sw = warp - kStage0;
+    constexpr bool PIECES = DH % 4 == 0 && DH >= 12;
+    constexpr int PPR = PIECES ? DH / 4 : 1;                        // 8-byte pieces per row
+    if constexpr (PIECES) {
+      for (int ob = 0; ob < OPB; ++ob) {
+        uint8_t* opnd = smem + L.opnd0 + ob * L.opnd_bytes;
+        for (int n = st; n < kN; n += kStageThreads) {
+          const int id_ = n % p.wd;
+          for (int e = DH; e < KS * 16; ++e)
+            *reinterpret_cast<__nv_bfloat16*>(opnd + L.q + (e >> 3) * (kN * 16) + n * 16 + (e & 7) * 2) =
+                (e - DH < p.wd && e - DH == id_) ? one : zero;
+        }
+        for (int j = st; j < NKT; j += kStageThreads) {
+          const int jd = j % p.wd;
+          for (int e = DH; e < KS * 16; ++e)
+            *reinterpret_cast<__nv_bfloat16*>(opnd + L.k + (e >> 3) * (NKT * 16) + j * 16 + (e & 7) * 2) =
+                (j < kN && e - DH < p.wd) ? __float2bfloat16(td_s[(e - DH) * p.wd + jd] * inv_scale) : zero;
+          for (int e = DH; e < DHP; ++e)
+            *reinterpret_cast<__nv_bfloat16*>(opnd + L.v + (j >> 3) * (NDC * 128) + (e >> 3) * 128 + (j & 7) * 16 + (e & 7) * 2) =
+                e == DH ? one : zero;
+        }
+      }
+    }
     int bw = blockIdx.x / p.heads;
     WS_PROF_DECL(8);          // 0 wait free, 1 loads + layout stores, 2 barrier, 3 selectors + bound, 4 windows
     for (int it = 0;; ++it) {
@@ -493,67 +522,79 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
       float kmax2 = 0.f;
       if (!stop) {
         const int b = bw / p.P, win = bw - b * p.P;
+        if (MASKED) {
+          if (p.sel != nullptr) {
+            // selector table of this window precomputed per geometry (pwa_attn_sel_table): ONE bulk copy, completion
+            // counted on the operand barrier (building it here cost the staging warps ~3 K clk per window)
+            if (st == 0) {
+              constexpr uint32_t kSelBytes = kIds * (kN / 4) * 4;
+              mbar_expect_tx(&bar[bOpFull + ob], kSelBytes);
+              bulk_g2s(sel_s, reinterpret_cast<const uint8_t*>(p.sel) + (size_t)win * kSelBytes, kSelBytes, &bar[bOpFull + ob]);
+            }
+          }
+          if (st < kN / 4)
+            reinterpret_cast<uint32_t*>(ids_s)[st] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[st];
+        }
         auto kv_off = [&](int j) {
           return j < kN ? ((size_t)bw * kN + j) * p.ldq + head * DH : ((size_t)b * p.I + (j - kN)) * p.ldp + head * DH;
         };
-        auto stage_q = [&](int t, const __nv_bfloat16 (&row)[DH]) {
-          const int n = t * 128 + st;
-          qn2[t] = sumsq_w<DH>(row);
-          qn2_s[n] = qn2[t];
-          const int id_ = n % p.wd;
-          __nv_bfloat16 extra[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
-          store_chunks_w<DH, KS>(Qs, kN * 16, n, row, extra, p.wd);
-        };
-        auto stage_k = [&](int j, const __nv_bfloat16 (&row)[DH]) {
-          const bool content = j < kN;
-          kmax2 = fmaxf(kmax2, sumsq_w<DH>(row));
-          const int jd = j % p.wd;
-          __nv_bfloat16 extra[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u)
-            extra[u] = (content && u < p.wd) ? __float2bfloat16(td_s[u * p.wd + jd] * inv_scale) : zero;
-          store_chunks_w<DH, KS>(Ks, NKT * 16, j, row, extra, p.wd);
-        };
-        auto stage_v = [&](int j, const __nv_bfloat16 (&row)[DH]) {
-#pragma unroll
-          for (int dc = 0; dc < NDC; ++dc) {
-            __align__(16) __nv_bfloat16 tmp[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              tmp[e] = (dc * 8 + e < DH) ? row[dc * 8 + e < DH ? dc * 8 + e : 0] : (dc * 8 + e == DH ? one : zero);
-            *reinterpret_cast<uint4*>(Vs + (j >> 3) * (NDC * 128) + dc * 128 + (j & 7) * 16) = *reinterpret_cast<const uint4*>(tmp);
+        if constexpr (PIECES) {
+          // asynchronous 8-byte copies (LDGSTS): every piece of the window in flight at once, no register staging -- the
+          // global round trip (~3 K clk under load) is paid once per window instead of once per register batch
+          auto cp8 = [](uint8_t* dst, const __nv_bfloat16* src) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+          };
+          const __nv_bfloat16* qb = (const __nv_bfloat16*)p.q + (size_t)bw * kN * p.ldq + head * DH;
+          const __nv_bfloat16* kb = (const __nv_bfloat16*)p.k + (size_t)bw * kN * p.ldq + head * DH;
+          const __nv_bfloat16* vb = (const __nv_bfloat16*)p.v + (size_t)bw * kN * p.ldq + head * DH;
+          const __nv_bfloat16* kpb = (const __nv_bfloat16*)p.kp + (size_t)b * p.I * p.ldp + head * DH;
+          const __nv_bfloat16* vpb = (const __nv_bfloat16*)p.vp + (size_t)b * p.I * p.ldp + head * DH;
+          for (int i = st; i < kN * PPR; i += kStageThreads) {       // content rows: Q, K, V share the (row, part) decode
+            const int row = i / PPR, part = i - row * PPR;
+            const uint32_t so = (uint32_t)(row * p.ldq + part * 4);
+            const uint32_t d16 = (uint32_t)(row * 16 + (part & 1) * 8);
+            cp8(Qs + (part >> 1) * (kN * 16) + d16, qb + so);
+            cp8(Ks + (part >> 1) * (NKT * 16) + d16, kb + so);
+            cp8(Vs + (row >> 3) * (NDC * 128) + (part >> 1) * 128 + (row & 7) * 16 + (part & 1) * 8, vb + so);
           }
-        };
-        if (MASKED && st < kN / 4)
-          reinterpret_cast<uint32_t*>(ids_s)[st] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[st];
-        if constexpr (DH <= 12) {
-          // every global load of this thread in flight before the first use (the round trips are what staging costs)
-          constexpr int KR = 3;                                      // key rows per thread: NKT <= 384 (I <= 128)
-          __nv_bfloat16 qrow[2][DH], krow[KR][DH], vrow[KR][DH];
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-            load_row_w<DH>((const __nv_bfloat16*)p.q + ((size_t)bw * kN + t * 128 + st) * p.ldq + head * DH, qrow[t]);
-#pragma unroll
-          for (int i = 0; i < KR; ++i) {
-            const int j = i * 128 + st;
-            if (j < NKT) {
-              load_row_w<DH>((const __nv_bfloat16*)(j < kN ? p.k : p.kp) + kv_off(j), krow[i]);
-              load_row_w<DH>((const __nv_bfloat16*)(j < kN ? p.v : p.vp) + kv_off(j), vrow[i]);
-            }
+          for (int i = st; i < p.I * PPR; i += kStageThreads) {      // prompt rows of K and V
+            const int r = i / PPR, part = i - r * PPR, row = kN + r;
+            const uint32_t so = (uint32_t)(r * p.ldp + part * 4);
+            cp8(Ks + (part >> 1) * (NKT * 16) + row * 16 + (part & 1) * 8, kpb + so);
+            cp8(Vs + (row >> 3) * (NDC * 128) + (part >> 1) * 128 + (row & 7) * 16 + (part & 1) * 8, vpb + so);
           }
-#pragma unroll
-          for (int t = 0; t < 2; ++t) stage_q(t, qrow[t]);
-#pragma unroll
-          for (int i = 0; i < KR; ++i) {
-            const int j = i * 128 + st;
-            if (j < NKT) {
-              stage_k(j, krow[i]);
-              stage_v(j, vrow[i]);
-            }
-          }
+          asm volatile("cp.async.wait_all;" ::: "memory");
         } else {
+          auto stage_q = [&](int t, const __nv_bfloat16 (&row)[DH]) {
+            const int n = t * 128 + st;
+            qn2[t] = sumsq_w<DH>(row);
+            qn2_s[n] = qn2[t];
+            const int id_ = n % p.wd;
+            __nv_bfloat16 extra[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) extra[u] = (u == id_) ? one : zero;
+            store_chunks_w<DH, KS>(Qs, kN * 16, n, row, extra, p.wd);
+          };
+          auto stage_k = [&](int j, const __nv_bfloat16 (&row)[DH]) {
+            const bool content = j < kN;
+            kmax2 = fmaxf(kmax2, sumsq_w<DH>(row));
+            const int jd = j % p.wd;
+            __nv_bfloat16 extra[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              extra[u] = (content && u < p.wd) ? __float2bfloat16(td_s[u * p.wd + jd] * inv_scale) : zero;
+            store_chunks_w<DH, KS>(Ks, NKT * 16, j, row, extra, p.wd);
+          };
+          auto stage_v = [&](int j, const __nv_bfloat16 (&row)[DH]) {
+#pragma unroll
+            for (int dc = 0; dc < NDC; ++dc) {
+              __align__(16) __nv_bfloat16 tmp[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e)
+                tmp[e] = (dc * 8 + e < DH) ? row[dc * 8 + e < DH ? dc * 8 + e : 0] : (dc * 8 + e == DH ? one : zero);
+              *reinterpret_cast<uint4*>(Vs + (j >> 3) * (NDC * 128) + dc * 128 + (j & 7) * 16) = *reinterpret_cast<const uint4*>(tmp);
+            }
+          };
 #pragma unroll
           for (int t = 0; t < 2; ++t) {
             __nv_bfloat16 row[DH];
@@ -568,30 +609,53 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
             stage_v(j, vrow);
           }
         }
-        kmax2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(kmax2)));   // non-negative floats order as uints
-        if (lane == 0) kmax_w[ob][sw] = __float_as_uint(kmax2);
       }
       WS_PROF(1);
-      stage_sync();                                               // ids, kmax partials, header of this operand set
+      stage_sync();                                               // pieces, ids, header of this operand set are in place
       WS_PROF(2);
-      const int next_bw = hdr->next_bw;
       if (!stop) {
-        if (MASKED) {
+        if constexpr (PIECES) {
+          // |q|^2 of this thread's two query rows and max |k|^2 over its key rows, from the staged copies
+          auto row_sumsq = [&](const uint8_t* base, uint32_t chunk_stride, int row) {
+            float a = 0.f;
+#pragma unroll
+            for (int part = 0; part < PPR; ++part) {
+              const uint2 w = *reinterpret_cast<const uint2*>(base + (part >> 1) * chunk_stride + row * 16 + (part & 1) * 8);
+              const float f0 = __uint_as_float(w.x << 16), f1 = __uint_as_float(w.x & 0xffff0000u);
+              const float f2 = __uint_as_float(w.y << 16), f3 = __uint_as_float(w.y & 0xffff0000u);
+              a = fmaf(f0, f0, fmaf(f1, f1, fmaf(f2, f2, fmaf(f3, f3, a))));
+            }
+            return a;
+          };
+#pragma unroll
+          for (int t = 0; t < 2; ++t) {
+            qn2[t] = row_sumsq(Qs, kN * 16, t * 128 + st);
+            qn2_s[t * 128 + st] = qn2[t];
+          }
+          for (int j = st; j < NKT; j += kStageThreads) kmax2 = fmaxf(kmax2, row_sumsq(Ks, NKT * 16, j));
+        }
+        kmax2 = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(kmax2)));   // non-negative floats order as uints
+        if (lane == 0) kmax_w[ob][sw] = __float_as_uint(kmax2);
+        if (MASKED && p.sel == nullptr) {
           // PRMT selectors: word w of row-id slot s covers keys 4w..4w+3 = packed pairs 2w (low half) and 2w+1 (high
           // half); a kept bf16 takes its own bytes (nibbles 1,0 / 3,2), a masked one those of the (e0,e0) operand
           for (int i = st; i < kIds * (kN / 4); i += kStageThreads) {
-            const int s = i / (kN / 4), w = i - s * (kN / 4);
+            const int s_ = i / (kN / 4), w = i - s_ * (kN / 4);
             const uint32_t idw = reinterpret_cast<const uint32_t*>(ids_s)[w];
             uint32_t sel = 0;
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const bool keep = id_slot_w((idw >> (8 * e)) & 0xffu) == s;
+              const bool keep = id_slot_w((idw >> (8 * e)) & 0xffu) == s_;
               const uint32_t nib = (e & 1) ? (keep ? 0x32u : 0x76u) : (keep ? 0x10u : 0x54u);
               sel |= nib << (((e & 1) ? 8 : 0) + ((e >> 1) ? 16 : 0));
             }
             sel_s[i] = sel;
           }
         }
+      }
+      stage_sync();                                               // partial key maxima
+      const int next_bw = hdr->next_bw;
+      if (!stop) {
         const float kmax = sqrtf(__uint_as_float(max(max(kmax_w[ob][0], kmax_w[ob][1]), max(kmax_w[ob][2], kmax_w[ob][3]))));
         if (st == 0) hdr->kmax = kmax;
         // stabiliser: upper bound of the row's logits; the row maximum is >= max_j bias - |q| max|k|, so the gap bounds how
@@ -615,7 +679,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
     }
     WS_PROF(3);
     if (st == 0) WS_PROF_OUT(16, 8);
-  } else if (warp < kIssue0 + 2) {
+  } else if (warp >= kIssue0 && warp < kIssue0 + 2) {
     // =============================================================================================
     // MMA issuer of group g: S runs two units ahead of PV; tcgen05.mma executes in issue order per thread
     // =============================================================================================
@@ -633,9 +697,12 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
         bool stop, need_open;
         uint32_t opnd;
       };
-      auto open_window = [&](Cur& c) {
+      // blocking = false: only if the operand set is already there (the S look-ahead must not stall the PVs of the units
+      // in flight behind a window that is still being staged)
+      auto open_window = [&](Cur& c, bool blocking) -> bool {
         const int ob = c.it % OPB;
-        mbar_wait(&bar[bOpFull + ob], (c.it / OPB) & 1);
+        if (blocking) mbar_wait(&bar[bOpFull + ob], (c.it / OPB) & 1);
+        else if (!__any_sync(0xffffffffu, mbar_try_wait(&bar[bOpFull + ob], (c.it / OPB) & 1))) return false;   // (warp-uniform)
         const WsHeader* hdr = reinterpret_cast<const WsHeader*>(smem + L.opnd0 + ob * L.opnd_bytes + L.hdr);
         c.stop = __shfl_sync(0xffffffffu, hdr->bw, 0) < 0;
         c.npass = __shfl_sync(0xffffffffu, hdr->exact, 0) ? 2 : 1;
@@ -643,6 +710,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
         c.u = 0;
         c.need_open = false;
         c.opnd = smem_u32(smem + L.opnd0 + ob * L.opnd_bytes);
+        return true;
       };
       auto advance = [&](Cur& c) {
         if (++c.u == n_units) {
@@ -654,18 +722,18 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
         }
       };
       Cur cs = {0, 0, 0, 1, false, true, 0u};
-      open_window(cs);
+      open_window(cs, true);
       Cur cp = cs;
       uint32_t ns = 0, np = 0, tcount = 0, obuf = 0;
       WS_PROF_DECL(8);        // 0 issue S (+ operand waits), 1 wait P, 2 wait O free, 3 issue PV
       for (;;) {
-        // ---- S of up to two units ahead ----
-        while (!cs.stop && ns < np + 2) {
+        // ---- S of up to three units ahead (all S buffers: two being exponentiated by the two sets, one waiting) ----
+        while (!cs.stop && ns < np + kNSB) {
           if (cs.need_open) {
             // with ONE operand buffer the next window is staged only after this one has retired completely: all of its
             // PVs must be issued before this thread may block on the next operand set
             if (OPB == 1 && np < ns) break;
-            open_window(cs);
+            if (!open_window(cs, np == ns)) break;                  // block only when nothing else is left to do
             if (cs.stop) break;
           }
           const uint32_t buf = ns % kNSB;
@@ -685,7 +753,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
               const uint64_t db = make_smem_desc(smem_u32(Ka) + koff, NKT * 16, 128);
               mma_ss(tg + buf * kUK, da, db, idesc, 1);
             }
-            mma_commit(&bar[bSFull + g * kNSB + buf]);
+            mma_commit(&bar[bSFull + g * 6 + ns % 6u]);
           }
           __syncwarp();
           ++ns;
@@ -696,7 +764,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
           continue;                                                 // (OPB == 1: the next window can be opened now)
         }
         // ---- PV of unit np ----
-        if (cp.need_open) open_window(cp);
+        if (cp.need_open) open_window(cp, true);
         const uint32_t buf = np % kNSB;
         WS_PROF(0);
         mbar_wait(&bar[bPReady + g * kNSB + buf], (np / kNSB) & 1);

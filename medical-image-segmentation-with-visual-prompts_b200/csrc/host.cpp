@@ -132,3 +132,30 @@ extern "C" int pwa_index_map(const pwa_geom* g, int which, int32_t* map) {
             }
   return PWA_OK;
 }
+
+// PRMT selector table of the shift mask for the tcgen05 attention kernels, per window: [P][28][N/4] uint32 in HOST
+// memory.  Row-id slot s (ids 0..26, 100 -> 27), word w covers keys 4w..4w+3 = packed bf16 pairs 2w (low half of the
+// word) and 2w+1 (high half): a key of the row's own region keeps its bytes (nibbles 1,0 / 3,2), any other key takes
+// those of the second PRMT operand (5,4 / 7,6).  It depends only on the geometry (swin_block.py:312-364 through
+// pwa_region_ids), so it is built once and cached next to the region ids; the forward kernel then fetches a window's
+// 7 KB with one bulk copy instead of rebuilding it for every (window, head).
+extern "C" int pwa_attn_sel_table(const uint8_t* ids, int P, int N, uint32_t* table) {
+  if (!ids || !table || P <= 0 || N <= 0 || N % 4 != 0) {
+    pwa::set_error("pwa_attn_sel_table: bad argument (P=%d N=%d)", P, N);
+    return PWA_ERR_ARG;
+  }
+  const int W = N / 4;
+  for (int p = 0; p < P; ++p)
+    for (int s = 0; s < 28; ++s)
+      for (int w = 0; w < W; ++w) {
+        uint32_t sel = 0;
+        for (int e = 0; e < 4; ++e) {
+          const uint32_t id = ids[(size_t)p * N + 4 * w + e];
+          const bool keep = (int)(id < 27u ? id : 27u) == s;
+          const uint32_t nib = (e & 1) ? (keep ? 0x32u : 0x76u) : (keep ? 0x10u : 0x54u);
+          sel |= nib << (((e & 1) ? 8 : 0) + ((e >> 1) ? 16 : 0));
+        }
+        table[((size_t)p * 28 + s) * W + w] = sel;
+      }
+  return PWA_OK;
+}

@@ -224,7 +224,33 @@ IMPL_AUTO, IMPL_F32, IMPL_TC = 0, 1, 2
 DYNAMIC_WORK = True
 
 
-def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0, seed_dev=None, work=None):
+_SEL_TABLES = {}
+
+
+def sel_table_for(ids: Optional[torch.Tensor]):
+    """Device copy of pwa_attn_sel_table(ids) (PRMT selectors of the shift mask, [P,28,N/4] int32), cached per ids tensor:
+    region ids are cached per geometry (Geometry.region_ids), so this is built once per geometry and device.  Returns None
+    when it cannot be built right now (first use inside a CUDA-graph capture): the kernel then builds its own."""
+    if ids is None or ids.dim() != 2 or ids.shape[1] % 4 != 0:
+        return None
+    key = (ids.data_ptr(), tuple(ids.shape), ids.device)
+    hit = _SEL_TABLES.get(key)
+    if hit is not None and hit[0] is ids:
+        return hit[1]
+    if torch.cuda.is_current_stream_capturing():
+        return None
+    import numpy as np
+    host = np.ascontiguousarray(ids.detach().cpu().numpy())
+    P, N = host.shape
+    tab = np.empty((P, 28, N // 4), dtype=np.uint32)
+    _lib.check(_lib.lib.pwa_attn_sel_table(host.ctypes.data, P, N, tab.ctypes.data), "pwa_attn_sel_table")
+    dev = torch.from_numpy(tab.view(np.int32)).to(ids.device)
+    _SEL_TABLES[key] = (ids, dev)          # (holding `ids` keeps its data_ptr from being recycled under the key)
+    return dev
+
+
+def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, ld_qkv=0, ld_p=0, seed_dev=None, work=None,
+                  sel=None):
     s = _lib.PwaAttnShape()
     s.B, s.P, s.C, s.heads, s.I = B, P, Cc, heads, I
     s.ld_qkv, s.ld_p = ld_qkv, ld_p
@@ -232,6 +258,7 @@ def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, l
     s.scale, s.p_drop, s.seed, s.offset = float(scale), float(p_drop), int(seed), int(offset)
     s.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
     s.work = None if work is None else work.data_ptr()      # forward only: per-head window counters
+    s.sel_table = None if sel is None else sel.data_ptr()   # forward only: precomputed shift-mask selectors
     return s
 
 
@@ -247,7 +274,8 @@ class _WindowAttention(torch.autograd.Function):
         out = torch.empty_like(q)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=q.device)
         work = torch.empty(heads, dtype=torch.int32, device=q.device) if DYNAMIC_WORK else None
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed, work=work)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed, work=work,
+                          sel=sel_table_for(ids) if q.dtype == torch.bfloat16 and impl != IMPL_F32 else None)
         with torch.cuda.device(q.device), _timed("attn_fwd", 1, 4.0 * B * P * N * (N + I) * Cc, q):
             rc = _lib.lib.pwa_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(kp), _ptr(vp), _ptr(th), _ptr(tw), _ptr(td),
                                        _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), C.byref(s), _dtype_code(q), impl,
@@ -502,7 +530,8 @@ class _WindowAttentionPacked(torch.autograd.Function):
         out = torch.empty((B, P, N, Cc), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((B, P, heads, N), dtype=torch.float32, device=qkv.device)
         work = torch.empty(heads, dtype=torch.int32, device=qkv.device) if DYNAMIC_WORK else None
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed, work=work)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed, work=work,
+                          sel=sel_table_for(ids) if qkv.dtype == torch.bfloat16 and impl != IMPL_F32 else None)
         q0 = qkv.data_ptr()
         p0 = 0 if kvp is None else kvp.data_ptr()
         vpp = C.c_void_p

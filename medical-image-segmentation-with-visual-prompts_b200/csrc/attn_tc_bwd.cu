@@ -469,13 +469,18 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
     // =============================================================================================
     // MMA issuers (one lane each)
     // =============================================================================================
-    if (lane == 0) {
+    // The WHOLE warp runs the control flow with warp-uniform values and only the tcgen05 instructions sit under
+    // elect.sync: the MMA operands then live in uniform registers.  With the loop inside `if (lane == 0)` ptxas wrapped
+    // every MMA in an ELECT + R2UR.BROADCAST waterfall loop, ~170 clk per instruction and issuing thread (this is what
+    // round 1 measured as "one thread issues a tcgen05.mma only every ~100-200 clk").
+    {
+      const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
       const uint32_t idescT = make_idesc_bf16(128, 64, 0, 0);       // S^T, dP^T : A K-major, B K-major, N = 64 rows
       const uint32_t idescDV = make_idesc_bf16(128, DHP, 0, 1);     // dV  : A tmem, B = dO MN-major
       const uint32_t idescDK = make_idesc_bf16(128, DKC, 0, 1);     // dK' : A tmem, B = Q' MN-major
       const uint32_t idescAUG = make_idesc_bf16(128, 16, 0, 1);     // dKaug
       const uint32_t idescDQ = make_idesc_bf16(128, DKC, 1, 1);     // dQ' : A = g smem MN-major, B = K' MN-major
-      const int role = warp - kIssue0;                              // 0 S, 1 V, 2 K, 3 A, 4 Q
+      const int role = __shfl_sync(0xffffffffu, warp - kIssue0, 0); // 0 S, 1 V, 2 K, 3 A, 4 Q
       int it = 0;
       for (int bw = bw0; bw < n_pairs; bw += stride, ++it) {
         const int ob = it % OPB;
@@ -493,24 +498,27 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             if (g >= NBUF) mbar_wait(&bar[bDoneC + buf], par ^ 1);
             tc_fence_after();
             STAMP(10 + unit);
+            if (elect_one_sync()) {
 #pragma unroll
-            for (int ks = 0; ks < KS; ++ks) {
-              const uint64_t da = make_smem_desc(Ks + ks * 2 * (NKR * 16) + kb * (128 * 16), NKR * 16, 128);
-              const uint64_t db = make_smem_desc(Qs + ks * 2 * (kN * 16) + qrow * 16, kN * 16, 128);
-              mma_ss(tmem + cS, da, db, idescT, ks > 0);
-            }
-            {
-              const uint64_t da = make_smem_desc(smem_u32(Ka) + kb * (128 * 16), NKR * 16, 128);
-              const uint64_t db = make_smem_desc(smem_u32(Qa) + qrow * 16, kN * 16, 128);
-              mma_ss(tmem + cS, da, db, idescT, 1);
-            }
+              for (int ks = 0; ks < KS; ++ks) {
+                const uint64_t da = make_smem_desc(Ks + ks * 2 * (NKR * 16) + kb * (128 * 16), NKR * 16, 128);
+                const uint64_t db = make_smem_desc(Qs + ks * 2 * (kN * 16) + qrow * 16, kN * 16, 128);
+                mma_ss(tmem + cS, da, db, idescT, ks > 0);
+              }
+              {
+                const uint64_t da = make_smem_desc(smem_u32(Ka) + kb * (128 * 16), NKR * 16, 128);
+                const uint64_t db = make_smem_desc(smem_u32(Qa) + qrow * 16, kN * 16, 128);
+                mma_ss(tmem + cS, da, db, idescT, 1);
+              }
 #pragma unroll
-            for (int ks = 0; ks < DHP / 16; ++ks) {
-              const uint64_t da = make_smem_desc(Vs + ks * 2 * (NKR * 16) + kb * (128 * 16), NKR * 16, 128);
-              const uint64_t db = make_smem_desc(dOs + ks * 2 * (kN * 16) + qrow * 16, kN * 16, 128);
-              mma_ss(tmem + cP, da, db, idescT, ks > 0);
+              for (int ks = 0; ks < DHP / 16; ++ks) {
+                const uint64_t da = make_smem_desc(Vs + ks * 2 * (NKR * 16) + kb * (128 * 16), NKR * 16, 128);
+                const uint64_t db = make_smem_desc(dOs + ks * 2 * (kN * 16) + qrow * 16, kN * 16, 128);
+                mma_ss(tmem + cP, da, db, idescT, ks > 0);
+              }
+              mma_commit(&bar[bFullS + buf]);
             }
-            mma_commit(&bar[bFullS + buf]);
+            __syncwarp();
             STAMP(100);
           } else if (role <= 3) {
             mbar_wait(&bar[bReady + buf], par);
@@ -522,6 +530,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             tc_fence_after();
             STAMP(10 + unit);
             // K = 64 rows = 4 k-steps; A = packed bf16 in TMEM: rows 0-31 live at cols 0-15, rows 32-63 at cols 32-47
+            if (elect_one_sync()) {
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const uint32_t acol = (t >> 1) * 32 + (t & 1) * 8;
@@ -539,6 +548,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             }
             mma_commit(&bar[bDoneC + buf]);
             if (u == 3) mma_commit(&bar[bKbDone]);                 // key block complete: the service warps drain dV / dK'
+            }
+            __syncwarp();
             STAMP(100);
           } else {
             // Every unit's phase is awaited in order, AND this issuer takes part in the recycling of the S^T ring: the dQ'
@@ -546,7 +557,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             // run four units ahead of this warp (e.g. while it waits for bDqFree at a window start), bReady[buf] would
             // complete two phases, and a parity wait two phases behind never returns (observed as a rare hang).
             mbar_wait(&bar[bReady + buf], par);
-            mbar_arrive(&bar[bDoneC + buf]);
+            if (elect_one_sync()) mbar_arrive(&bar[bDoneC + buf]);
+            __syncwarp();
             STAMP(10 + unit);
             if (hf == 0) continue;
             // dQ'[mt] += g[128 rows x nk keys] . K'[kb]
@@ -555,13 +567,19 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             const uint32_t Gs = smem_u32(smem + L.g + gs * (128 * 128 * 2));
             if (kb == 0 && it > 0) mbar_wait(&bar[bDqFree], (it - 1) & 1);
             tc_fence_after();
-            for (int t = 0; t < nk / 16; ++t) {
-              const uint64_t da = make_smem_desc(Gs + t * 256, 128, 2048);
-              const uint64_t db = make_smem_desc(Ks + (kb * 128 + t * 16) * 16, 128, NKR * 16);
-              mma_ss(tmem + cDQ + mt * DKC, da, db, idescDQ, (kb > 0) | (t > 0));
+            if (elect_one_sync()) {
+#pragma unroll
+              for (int t = 0; t < 8; ++t) {
+                if (t * 16 < nk) {
+                  const uint64_t da = make_smem_desc(Gs + t * 256, 128, 2048);
+                  const uint64_t db = make_smem_desc(Ks + (kb * 128 + t * 16) * 16, 128, NKR * 16);
+                  mma_ss(tmem + cDQ + mt * DKC, da, db, idescDQ, (kb > 0) | (t > 0));
+                }
+              }
+              mma_commit(&bar[bDoneQ + gs]);
+              if (kb == n_kb - 1 && mt == 1) mma_commit(&bar[bWinQ]);  // window complete: the service warps drain dQ'
             }
-            mma_commit(&bar[bDoneQ + gs]);
-            if (kb == n_kb - 1 && mt == 1) mma_commit(&bar[bWinQ]);  // window complete: the service warps drain dQ'
+            __syncwarp();
             STAMP(100);
           }
         }

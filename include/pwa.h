@@ -17,6 +17,8 @@
  *   - every launch goes to the cudaStream_t passed in (void* so that C callers need no CUDA headers).
  *   - return 0 on success, <0 on error; pwa_last_error() returns a thread-local message.
  *   - the device is the caller's current device (one process per GPU).
+ *   - debug-only entry points (clock64 timelines of the attention kernels) live in include/pwa_debug.h and exist only in
+ *     libraries built with `make TIMELINE=1`.
  *   - re-entrant and thread-safe (no global mutable state besides one-time kernel attribute setup).
  *   - there is NO CPU fallback: device entry points fail with PWA_ERR_CUDA when no GPU is present.
  */
@@ -112,6 +114,13 @@ int pwa_gather_rows(const void* src_a, const void* src_b, void* dst, const int32
  * torch autograd in the reference): dW = dy^T x is computed as S batched slices of the token axis with fp32 partials. */
 int pwa_colsum_f32(const float* src, float* dst, int S, int64_t n, void* stream);
 
+/* y[i] = keep(i) ? x[i] / keep_rate : 0 for i < n, keep(i) a counter-based hash of the two uint32 words at seed_dev (DEVICE
+ * memory) and i; rate in steps of 1/256.  Replaces nn.Dropout(proj_drop) after the attention output projection
+ * (window_attention.py:33,60).  The same call on dy is the backward.  No generator state is involved, so an activation-
+ * checkpointed block recomputes the same mask and a captured CUDA graph gets fresh masks whenever the seed words change.
+ * x == y is allowed; both 16-byte aligned. */
+int pwa_dropout(const void* x, void* y, int64_t n, float p_drop, const void* seed_dev, int dtype, void* stream);
+
 /* ---- (b) fused prompted window attention, forward -------------------------------------------- */
 
 typedef struct pwa_attn_shape {
@@ -183,7 +192,7 @@ int pwa_bias_tables_bwd(const float* enc_h, const float* enc_w, const float* enc
 
 /* ---- LayerNorm over the channel axis of window tokens, fused with the surrounding residual adds ----- */
 
-/* s = x (+ res) ; y = LayerNorm(s) * gamma + beta over the last axis (C, C % 4 == 0, C <= 1024), rows x C
+/* s = x (+ res) ; y = LayerNorm(s) * gamma + beta over the last axis (C, C % 4 == 0, C <= 2048), rows x C
  * row-major.  Replaces nn.LayerNorm(eps=1e-6) at swin_block.py:216 (attn_norm) and :227 (mlp_norm) together
  * with the residual add of :222.  res / sum_out may be NULL (plain LayerNorm).  gamma, beta fp32.
  * mean, rstd: fp32 [rows], saved for the backward. */
@@ -203,11 +212,6 @@ int pwa_ln_bwd(const void* dy, const void* x, const float* gamma, const float* m
 int pwa_ln_bwd2(const void* dy, const void* x, const float* gamma, const float* mean, const float* rstd,
                 const void* dres, void* dx, float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
                 int64_t rows, int C, int dtype, void* stream);
-
-/* Test infrastructure only: with PWA_TIMELINE=1 in the environment and a library built with `make TIMELINE=1`, CTA 0 of
- * the tcgen05 forward kernel records clock64 stamps; this copies them to the host (tools/timeline_fwd.py).  Returns the
- * number of bytes copied, 0 when no timeline exists. */
-int pwa_debug_fwd_timeline(void* host_dst, int bytes);
 
 /* 1 iff the bf16 tcgen05 kernel supports this shape (else impl=0 falls back to the fp32-math kernel). */
 int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype);

@@ -36,8 +36,10 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
   p.ldq = s->ld_qkv > 0 ? s->ld_qkv : s->C;
   p.ldp = s->ld_p > 0 ? s->ld_p : s->C;
   PWA_CHECK_ARG(p.ldq >= s->C && p.ldp >= s->C, "%s: row strides must be >= C", who);
+#ifdef PWA_TIMELINE_BUILD
   static const int dbg = getenv("PWA_TIMELINE") != nullptr;
   p.debug = dbg;
+#endif
   return PWA_OK;
 }
 
@@ -45,14 +47,17 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
 
 using namespace pwa;
 
+#ifdef PWA_TIMELINE_BUILD
+// Debug builds only (`make TIMELINE=1`, include/pwa_debug.h): the product library neither exports this symbol nor contains
+// the allocation / synchronous copy below -- its entry points never allocate or synchronise (include/pwa.h).
 static void* g_fwd_timeline = nullptr;
 
-/* test infrastructure: copy the forward kernel's debug timeline (PWA_TIMELINE=1) to the host; returns bytes copied */
 extern "C" int pwa_debug_fwd_timeline(void* host_dst, int bytes) {
   if (!g_fwd_timeline || bytes > (1 << 20)) return 0;
   if (cudaMemcpy(host_dst, g_fwd_timeline, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
   return bytes;
 }
+#endif
 
 extern "C" int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype) {
   AttnParams p = {};
@@ -73,13 +78,15 @@ extern "C" int pwa_attn_fwd(const void* q, const void* k, const void* v, const v
   p.th = th; p.tw = tw; p.td = td; p.tok = tok; p.ids = ids;
   p.out = out; p.lse = lse;
   cudaStream_t st = (cudaStream_t)stream;
-  if (p.debug) {   // PWA_TIMELINE=1 (test infrastructure): CTA 0 of the forward kernel writes clock64 stamps here
+#ifdef PWA_TIMELINE_BUILD
+  if (p.debug) {   // PWA_TIMELINE=1 (debug build): CTA 0 of the forward kernel writes clock64 stamps / cycle counters here
     static void* tl = nullptr;
     if (!tl) PWA_CUDA_OK(cudaMalloc(&tl, 1 << 20));
     PWA_CUDA_OK(cudaMemsetAsync(tl, 0, 1 << 20, st));
     p.delta = (float*)tl;
     g_fwd_timeline = tl;
   }
+#endif
   const bool tc_ok = attn_tc_supported(p, dtype);
   if (impl == 2 && !tc_ok) {
     set_error("pwa_attn_fwd: tcgen05 kernel does not support this shape/dtype");

@@ -524,18 +524,12 @@ static int launch_vec(bool is_partition, const void* src, const void* src2, void
   size_t smem = (size_t)p.ww * p.Dp * p.pitch * 4;
   dim3 grid((unsigned)((size_t)p.B * p.Hp * p.P2 * p.nchunk));
   if (is_partition) {
-    static bool attr_done = false;  // benign race: idempotent
-    if (!attr_done) {
-      PWA_CUDA_OK(cudaFuncSetAttribute(partition_vec_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
-    }
+    // (the attribute is per DEVICE: set it on every launch -- cheap, capture-safe, correct for one process driving several GPUs)
+    PWA_CUDA_OK(cudaFuncSetAttribute(partition_vec_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     partition_vec_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
   } else {
-    static bool attr_done = false;
-    if (!attr_done) {
-      PWA_CUDA_OK(cudaFuncSetAttribute(reverse_vec_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
-    }
+    // (the attribute is per DEVICE: set it on every launch -- cheap, capture-safe, correct for one process driving several GPUs)
+    PWA_CUDA_OK(cudaFuncSetAttribute(reverse_vec_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     reverse_vec_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (const uint32_t*)src2, (uint32_t*)dst, p);
   }
   PWA_CUDA_OK(cudaGetLastError());
@@ -547,18 +541,12 @@ static int launch_fast(bool is_partition, const void* src, const void* src2, voi
   size_t smem = (size_t)p.ww * p.Dp * p.pitch * 4;
   dim3 grid((unsigned)((size_t)p.B * p.Hp * p.P2 * p.nchunk));
   if (is_partition) {
-    static bool attr_done = false;  // benign race: idempotent
-    if (!attr_done) {
-      PWA_CUDA_OK(cudaFuncSetAttribute(partition_fast_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
-    }
+    // (the attribute is per DEVICE: set it on every launch -- cheap, capture-safe, correct for one process driving several GPUs)
+    PWA_CUDA_OK(cudaFuncSetAttribute(partition_fast_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     partition_fast_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (uint32_t*)dst, p);
   } else {
-    static bool attr_done = false;
-    if (!attr_done) {
-      PWA_CUDA_OK(cudaFuncSetAttribute(reverse_fast_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr_done = true;
-    }
+    // (the attribute is per DEVICE: set it on every launch -- cheap, capture-safe, correct for one process driving several GPUs)
+    PWA_CUDA_OK(cudaFuncSetAttribute(reverse_fast_kernel<EB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     reverse_fast_kernel<EB><<<grid, 256, smem, st>>>((const uint32_t*)src, (const uint32_t*)src2, (uint32_t*)dst, p);
   }
   PWA_CUDA_OK(cudaGetLastError());

@@ -16,8 +16,13 @@ import torch.distributed as dist
 
 
 class BucketedGradSync:
-    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None):
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20, group=None, overlap: bool = True):
+        """overlap=True: a bucket's all-reduce starts (in bucket order) as soon as its last gradient is accumulated --
+        exactly ONE backward per finish().  overlap=False: every collective is issued from finish(), any number of
+        backward passes (gradient accumulation) in between."""
         self.group = group
+        self.overlap = overlap
+        self._next = 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         # reverse order ~ the order in which backward produces gradients
@@ -45,8 +50,18 @@ class BucketedGradSync:
         def hook(_param):
             b = self.bucket_of[i]
             self._ready[b] += 1
-            if self._ready[b] == len(self.buckets[b]):
-                self._launch(b)
+            if self._ready[b] > len(self.buckets[b]):
+                # a second backward before finish() (gradient accumulation): the bucket's all-reduce of the first
+                # backward is already in flight and would overwrite the accumulated gradients in finish()
+                raise RuntimeError("BucketedGradSync: backward() ran twice before finish(); with gradient accumulation "
+                                   "construct it with overlap=False (collectives are then issued from finish() only)")
+            # Buckets are launched strictly in bucket order on every rank: a bucket whose hooks all fired waits for its
+            # predecessors (ranks with different sets of unused parameters would otherwise issue the collectives in
+            # different orders, which mismatches or hangs NCCL)
+            if self.overlap:
+                while self._next < len(self.buckets) and self._ready[self._next] == len(self.buckets[self._next]):
+                    self._launch(self._next)
+                    self._next += 1
         return hook
 
     def _launch(self, b):
@@ -63,9 +78,9 @@ class BucketedGradSync:
         (parameters without gradient this step), waits, averages and scatters back into .grad."""
         if self.world == 1:
             return
-        for b in range(len(self.buckets)):
-            if self._work[b] is None:
-                self._launch(b)
+        for b in range(self._next, len(self.buckets)):     # in bucket order, like the hooks
+            self._launch(b)
+        self._next = 0
         for b, idxs in enumerate(self.buckets):
             self._work[b].wait()
             flat = self._flat[b].div_(self.world)

@@ -262,6 +262,33 @@ def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, l
     return s
 
 
+def _check_attn_side_inputs(B, P, N, Cc, dtype, kp, vp, kp_width, th, tw, td, tok, ids, heads, ws):
+    """The kernels index these tensors with raw pointers: every shape / dtype the reference would reject (at its
+    torch.cat / broadcast) is rejected here, before a launch could read out of bounds."""
+    ws = tuple(int(w) for w in ws)
+    if len(ws) != 3 or ws[0] * ws[1] * ws[2] != N:
+        raise ValueError(f"window {ws} does not hold N = {N} tokens")
+    for name, t, w in (("th", th, ws[0]), ("tw", tw, ws[1]), ("td", td, ws[2])):
+        if tuple(t.shape) != (heads, w, w):
+            raise ValueError(f"bias table {name} must be [{heads},{w},{w}], got {tuple(t.shape)}")
+    I = 0
+    if kp is not None:
+        if kp.dim() != 3 or kp.shape[0] != B or kp.shape[2] != kp_width * Cc or kp.dtype != dtype:
+            raise ValueError(f"prompt keys/values must be [{B}, I, {kp_width * Cc}] {dtype}, got {tuple(kp.shape)} {kp.dtype} "
+                             "(one row set per sample)")
+        I = kp.shape[1]
+        if vp is not None and (vp.shape != kp.shape or vp.dtype != dtype):
+            raise ValueError(f"vp {tuple(vp.shape)} does not match kp {tuple(kp.shape)}")
+        if kp_width == 1 and vp is None:
+            raise ValueError("vp missing")
+        if tok is None or tuple(tok.shape) != (heads, I):
+            raise ValueError(f"prompt-token bias must be [{heads},{I}]")
+    elif vp is not None:
+        raise ValueError("vp given without kp")
+    if ids is not None and (ids.dtype != torch.uint8 or tuple(ids.shape) != (P, N)):
+        raise ValueError(f"region ids must be uint8 [{P},{N}], got {ids.dtype} {tuple(ids.shape)}")
+
+
 class _WindowAttention(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q, k, v, kp, vp, th, tw, td, tok, ids, heads, ws, scale, impl, p_drop=0.0, seed=None):
@@ -317,6 +344,10 @@ def prompted_window_attention(q, k, v, kp, vp, th, tw, td, tok, ids, heads: int,
     _require_cuda(q, k, v, kp, vp, th, tw, td, tok, ids)
     if q.shape[-1] % heads != 0:
         raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
+    if q.dim() != 4 or k.shape != q.shape or v.shape != q.shape or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise ValueError(f"prompted_window_attention: q, k, v must be equal-shaped [B,P,N,C], got {tuple(q.shape)}, "
+                         f"{tuple(k.shape)}, {tuple(v.shape)}")
+    _check_attn_side_inputs(q.shape[0], q.shape[1], q.shape[2], q.shape[3], q.dtype, kp, vp, 1, th, tw, td, tok, ids, heads, ws)
     if p_drop > 0 and seed is None:
         seed = new_dropout_seed(q.device)
     return _WindowAttention.apply(q, k, v, kp, vp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl, float(p_drop), seed)
@@ -576,10 +607,46 @@ class _WindowAttentionPacked(torch.autograd.Function):
         return dqkv, dkvp, dth, dtw, dtd, dtok, None, None, None, None, None, None, None
 
 
-def new_dropout_seed(device) -> torch.Tensor:
-    """Two 32-bit seed words ON THE DEVICE for one attention-dropout call (forward and backward share them).  Drawn
-    with a CUDA RNG op, so torch.manual_seed governs it and a captured CUDA graph gets fresh words on every replay."""
-    return torch.randint(0, 2 ** 31 - 1, (2,), dtype=torch.int32, device=device)
+def new_dropout_seed(device, words: int = 2) -> torch.Tensor:
+    """32-bit seed words ON THE DEVICE (two per dropout site: forward and backward share them).  Drawn with a CUDA RNG op,
+    so torch.manual_seed governs it and a captured CUDA graph gets fresh words on every replay."""
+    return torch.randint(0, 2 ** 31 - 1, (words,), dtype=torch.int32, device=device)
+
+
+class _SeededDropout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p_drop, seed):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device), _timed("dropout", 1, 2.0 * x.numel() * x.element_size(), x):
+            rc = _lib.lib.pwa_dropout(_ptr(x), _ptr(y), x.numel(), float(p_drop), _ptr(seed), _dtype_code(x), _stream(x))
+        _lib.check(rc, "pwa_dropout")
+        ctx.save_for_backward(seed)
+        ctx.p_drop = float(p_drop)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (seed,) = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        with torch.cuda.device(dy.device), _timed("dropout", 1, 2.0 * dy.numel() * dy.element_size(), dy):
+            rc = _lib.lib.pwa_dropout(_ptr(dy), _ptr(dx), dy.numel(), ctx.p_drop, _ptr(seed), _dtype_code(dy), _stream(dy))
+        _lib.check(rc, "pwa_dropout")
+        return dx, None, None
+
+
+def seeded_dropout(x: torch.Tensor, p_drop: float, seed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Dropout whose mask is a pure function of two device seed words and the element index (csrc/dropout.cu): the
+    reference's nn.Dropout(proj_drop) (window_attention.py:60), safe under activation checkpointing inside a CUDA graph."""
+    _require_cuda(x, seed)
+    if p_drop <= 0.0:
+        return x
+    if seed is None:
+        seed = new_dropout_seed(x.device)
+    if seed.dtype != torch.int32 or seed.numel() < 2:
+        raise ValueError("seeded_dropout: seed must be an int32 tensor with two words")
+    return _SeededDropout.apply(x, float(p_drop), seed)
 
 
 def prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads: int, ws: Sequence[int], scale: float,
@@ -590,6 +657,10 @@ def prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads: int,
     _require_cuda(qkv, kvp, th, tw, td, tok, ids)
     if qkv.shape[-1] % (3 * heads) != 0:
         raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
+    if qkv.dim() != 4:
+        raise ValueError(f"prompted_window_attention_packed: qkv must be [B,P,N,3C], got {tuple(qkv.shape)}")
+    _check_attn_side_inputs(qkv.shape[0], qkv.shape[1], qkv.shape[2], qkv.shape[3] // 3, qkv.dtype, kvp, None, 2, th, tw, td, tok,
+                            ids, heads, ws)
     if p_drop > 0 and seed is None:
         seed = new_dropout_seed(qkv.device)
     return _WindowAttentionPacked.apply(qkv, kvp, th, tw, td, tok, ids, heads, tuple(ws), scale, impl, float(p_drop), seed)

@@ -56,8 +56,8 @@ class WindowAttention(nn.Module):
         """q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
         appended to the keys/values of every window; pos_bias: BiasTables; mask: uint8 region ids [P,N]
         (mask[p,i,j] = ids[p,i]==ids[p,j]) or None; lowp: optional {'qkv','kv','proj'} weights already cast to the
-        compute dtype (SwinTransformerBlock packs them once per forward); drop_seed: optional int32 [2] device tensor
-        with the attention-dropout seed words (drawn here when absent); prompt_kv: `project_prompts(prompts, lowp)`
+        compute dtype (SwinTransformerBlock packs them once per forward); drop_seed: optional int32 [4] device tensor:
+        words 0-1 seed the attention dropout, words 2-3 the projection dropout (drawn here when absent); prompt_kv: `project_prompts(prompts, lowp)`
         computed by the caller ahead of time (self-attention path only), instead of `prompts`.  Returns [B,P,N,C]."""
         if pos_bias is None or not isinstance(pos_bias, BiasTables):
             raise NotImplementedError("WindowAttention on the fused kernels takes the compact BiasTables form of the "
@@ -66,6 +66,14 @@ class WindowAttention(nn.Module):
         # The mask comes from a counter-based hash of (seed words, sample, window, head, query, key); it cannot be the
         # reference's torch Philox stream (that is indexed over a dense [B,P,h,N',N'] tensor which does not exist here).
         p_drop = float(self.attn_drop.p) if self.training else 0.0
+        p_proj = float(self.proj_drop.p) if self.training else 0.0
+        if (p_drop > 0 or p_proj > 0) and drop_seed is None:
+            drop_seed = PF.new_dropout_seed(q.device, 4)
+        proj_seed = None
+        if drop_seed is not None:
+            if drop_seed.numel() < 4:
+                raise ValueError("WindowAttention: drop_seed must hold four int32 words (attention, projection)")
+            drop_seed, proj_seed = drop_seed[:2], drop_seed[2:4]
         impl = self.impl
         if q is k and k is v:
             # self-attention (the only way the block calls it): ONE fused [C -> 3C] projection GEMM; the kernels
@@ -87,4 +95,6 @@ class WindowAttention(nn.Module):
                                              mask, self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop, seed=drop_seed)
         o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'), bias_grad=proj_bias_grad,
                             lowp_bias=(lowp or {}).get('proj_b'))
-        return self.proj_drop(o)
+        # projection dropout (reference :60): seeded kernel instead of nn.Dropout, so that a checkpointed block inside a
+        # CUDA graph recomputes the same mask without touching the generator state (csrc/dropout.cu)
+        return PF.seeded_dropout(o, p_proj, proj_seed) if p_proj > 0 else o

@@ -213,6 +213,8 @@ class SwinTransformerBlock(nn.Module):
         lowp = self._lowp_weights(cdt)
         kvp = None
         if p is not None:
+            if p.dim() != 3 or p.shape[-1] != c:
+                raise ValueError(f"SwinTransformerBlock: prompt tokens must be [B, I, {c}], got {tuple(p.shape)}")
             if PF.layer_norm_supported(c):
                 prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6)
             else:
@@ -262,20 +264,17 @@ class SwinTransformerBlock(nn.Module):
 
     def _tokens_forward_ckpt(self, xw, p, geom, cdt, side=None):
         """_tokens_forward, under activation checkpointing when `use_checkpoint` is set (reference :257-260).  The
-        attention-dropout seed words are drawn OUTSIDE the checkpointed region and passed in, so the recomputation sees
-        the same mask without saving / restoring the CUDA generator state (which a graph capture cannot do); only
-        torch's own proj_drop needs the generator state preserved."""
+        seed words of the attention dropout AND of the projection dropout (both seeded kernels, csrc/attn.cuh and
+        csrc/dropout.cu) are drawn OUTSIDE the checkpointed region and passed in, so the recomputation sees the same masks
+        without saving / restoring the CUDA generator state -- which a graph capture cannot do.  The reference's example
+        config (use_checkpoint, attn_drop = proj_drop = 0.1) therefore runs inside a captured step."""
         if not (self.use_checkpoint and torch.is_grad_enabled()):
             return self._tokens_forward(xw, p, geom, cdt, None, side)
         seed = None
-        if self.training and self.attn.attn_drop.p > 0:
-            seed = PF.new_dropout_seed(xw.device)
-        need_rng = self.training and self.attn.proj_drop.p > 0
-        if need_rng and torch.cuda.is_current_stream_capturing():
-            raise RuntimeError("use_checkpoint with proj_drop > 0 cannot be captured into a CUDA graph: the recomputation "
-                               "needs the generator state restored (capture without checkpointing, or set proj_drop = 0)")
+        if self.training and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):
+            seed = PF.new_dropout_seed(xw.device, 4)
         return checkpoint.checkpoint(self._tokens_forward, xw, p, geom, cdt, seed, side, use_reentrant=False,
-                                     preserve_rng_state=need_rng)
+                                     preserve_rng_state=False)
 
     def _geometry(self, dims):
         shift_cfg = tuple(self.shift_size) if self.shift_size is not None else (0, 0, 0)

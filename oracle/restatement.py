@@ -292,6 +292,31 @@ def dropout_keep_factor_torch(seed_words, bw0, n_bw, num_heads, N, NK, p_drop, d
     return (num >= t).to(torch.float64) * (256.0 / (256 - t))
 
 
+def elementwise_dropout_keep_factor(seed_words, n, p_drop):
+    """The projection-dropout mask of csrc/dropout.cu (pwa_dropout) restated: float64 [n] of 0 / (1/keep_rate).  One
+    32-bit hash per 4 consecutive elements (two avalanche mixes of seed and quad index), one byte per element, kept iff
+    byte >= round(256 p).  Stands for nn.Dropout(proj_drop) (window_attention.py:60): same distribution, different
+    stream (torch's Philox)."""
+    M = np.uint64(0xFFFFFFFF)
+    u = np.uint64
+
+    def mix(x):
+        x = x & M
+        x ^= x >> u(16); x = (x * u(0x21f0aaad)) & M
+        x ^= x >> u(15); x = (x * u(0x735a2d97)) & M
+        x ^= x >> u(15)
+        return x
+
+    t = _drop_threshold(p_drop)
+    s0, s1 = (u(int(w) & 0xFFFFFFFF) for w in seed_words)
+    i = np.arange(n, dtype=np.uint64)
+    q = i >> u(2)
+    h = mix(s0 + ((q & M) * u(0x9E3779B1) & M) + (((q >> u(32)) * u(0x85EBCA77)) & M)) ^ s1
+    bits = mix(h)
+    byte = (bits >> (u(8) * (i & u(3)))) & u(0xFF)
+    return torch.from_numpy((byte >= u(t)).astype(np.float64) * (256.0 / (256 - t)))
+
+
 def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads, drop=None):
     """q,k,v [B,P,N,C]; kp,vp [B,I,C] or None; bias [h,N,N+I]; ids int [P,N] or None.
     window_attention.py:45-59: logits = (q.k^T*scale + bias) * mask, softmax over keys, [dropout,] @ v.
@@ -331,9 +356,10 @@ def split_block_params(sd: Dict[str, torch.Tensor]):
 
 
 def block_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, p: Optional[torch.Tensor],
-                  ws, shift_cfg, num_heads: int) -> torch.Tensor:
+                  ws, shift_cfg, num_heads: int, attn_drop: float = 0.0, proj_drop: float = 0.0) -> torch.Tensor:
     """One SwinTransformerBlock.forward_attn_mlp (swin_block.py:145-255) from a state dict
-    with the reference's key names.  No dropout (eval / p=0)."""
+    with the reference's key names.  attn_drop / proj_drop > 0: torch's own dropout on the attention probabilities and
+    on the projection output, as the reference applies it (window_attention.py:57,60) -- used by the CPU timing arm."""
     ws = tuple(ws)
     dims = tuple(x.shape[2:])
     C = x.shape[1]
@@ -358,8 +384,15 @@ def block_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, p: Optional[torc
         kp = lp @ sd["attn.to_k.weight"].t()
         vp = lp @ sd["attn.to_v.weight"].t()
     dh = C // num_heads
-    o = prompted_window_attention(q, k, v, kp, vp, bias, ids, dh ** -0.5, num_heads)
-    y = o @ sd["attn.proj.weight"].t() + sd["attn.proj.bias"] + xw             # :60, :222
+    drop = None
+    if attn_drop > 0:
+        B_, P_, N_ = q.shape[:3]
+        drop = F.dropout(torch.ones(B_, P_, num_heads, N_, N_ + I, dtype=q.dtype, device=q.device), attn_drop, True)
+    o = prompted_window_attention(q, k, v, kp, vp, bias, ids, dh ** -0.5, num_heads, drop=drop)
+    a = o @ sd["attn.proj.weight"].t() + sd["attn.proj.bias"]                  # :60
+    if proj_drop > 0:
+        a = F.dropout(a, proj_drop, True)
+    y = a + xw                                                                  # :222
     z = F.layer_norm(y, (C,), sd["mlp_norm.weight"], sd["mlp_norm.bias"], 1e-6)
     y = y + z @ sd["mlp.weight"].t() + sd["mlp.bias"]                          # :227 single Linear
     return reverse_tokens(y, dims, ws, shift, pads)
@@ -388,14 +421,15 @@ def patch_merging_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, merge_la
     return t.permute(0, 4, 1, 2, 3).contiguous()
 
 
-def pair_forward(sd: Dict[str, torch.Tensor], x, p_pair, ws, num_heads, down: bool, merge_last_dim: bool = True):
+def pair_forward(sd: Dict[str, torch.Tensor], x, p_pair, ws, num_heads, down: bool, merge_last_dim: bool = True,
+                 attn_drop: float = 0.0, proj_drop: float = 0.0):
     """ConsecutiveSwinBlocks.forward (swin_block.py:66-71): unshifted block, then block
     shifted by ws//2, then optional PatchMerging."""
     ws = tuple(ws)
     shift = tuple(w // 2 for w in ws)
     for i, sh in enumerate(((0, 0, 0), shift)):
         sub = {k[len(f"swin_blocks.{i}."):]: v for k, v in sd.items() if k.startswith(f"swin_blocks.{i}.")}
-        x = block_forward(sub, x, p_pair[i], ws, sh, num_heads)
+        x = block_forward(sub, x, p_pair[i], ws, sh, num_heads, attn_drop, proj_drop)
     if down:
         sub = {k[len("merge."):]: v for k, v in sd.items() if k.startswith("merge.")}
         x = patch_merging_forward(sub, x, merge_last_dim)

@@ -733,3 +733,62 @@ def test_token_split_weight_gradient(T, co, ci):
     ref = dy.double().t() @ x.double()
     assert dw.dtype == torch.float32 and dw.shape == (co, ci)
     assert (dw.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [4096, 1000003])
+def test_seeded_projection_dropout_matches_oracle_mask(dtype, n):
+    """pwa_dropout (the seeded stand-in for nn.Dropout(proj_drop), window_attention.py:60): exactly the mask the oracle
+    restates, inverse-keep-rate scaling, and backward = the same mask on the upstream gradient."""
+    words = [424242, -77]
+    seed = torch.tensor(words, dtype=torch.int32, device=DEV)
+    x = torch.randn(n, device=DEV).to(dtype).requires_grad_(True)
+    y = PF.seeded_dropout(x, 0.1, seed)
+    keep = R.elementwise_dropout_keep_factor(words, n, 0.1).to(DEV)
+    assert abs((keep == 0).double().mean().item() - 26 / 256) < 0.01
+    exp = (x.detach().double() * keep).to(dtype)
+    assert rel_linf(y, exp) < (1e-6 if dtype == torch.float32 else 4e-3)
+    assert torch.equal(y == 0, (keep == 0) | (x.detach() == 0))
+    g = torch.randn(n, device=DEV).to(dtype)
+    y.backward(g)
+    assert rel_linf(x.grad, (g.double() * keep).to(dtype)) < (1e-6 if dtype == torch.float32 else 4e-3)
+
+
+def test_reference_training_config_inside_a_cuda_graph():
+    """configurations/example_configs.yml:17-19 (use_checkpoint, attn_drop = proj_drop = 0.1) captured into ONE CUDA
+    graph: the recomputation must see the forward's masks (seed words drawn outside the checkpointed region), every
+    replay must draw new masks, and the gradients must match an eager run with the same seed words."""
+    from pwa_b200.graphs import GraphedStep
+    torch.manual_seed(13)
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=48, num_heads=4, pos_bias_embed_dim=64, max_prompts=1,
+                                          tokens_per_prompt=64, window_size=(8, 8, 4), down=True, use_checkpoint=True,
+                                          attn_drop=0.1, proj_drop=0.1).to(DEV).train()
+    prompts = [torch.nn.Parameter(0.2 * torch.randn(64, 48, device=DEV)) for _ in range(2)]
+    params = list(pair.parameters()) + prompts
+
+    def step(x):
+        p = tuple(t.to(x.dtype).unsqueeze(0).expand(x.shape[0], -1, -1) for t in prompts)
+        loss = pair(x, p).float().square().mean()
+        loss.backward()
+        return loss.detach()
+
+    x = torch.randn(2, 48, 16, 16, 8, device=DEV).bfloat16()
+    g = GraphedStep(step, [x.clone().requires_grad_(True)], params)
+    l1 = g(x).clone()
+    g1 = [p.grad.clone() for p in params]
+    l2 = g(x).clone()
+    assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() != l2.item()          # new masks on every replay
+    assert all(torch.isfinite(a).all() for a in g1)
+    # checkpointed == plain for identical masks: eager, same generator state for both
+    outs = []
+    for ckpt in (True, False):
+        for blk in pair.swin_blocks:
+            blk.use_checkpoint = ckpt
+        pair.use_checkpoint = ckpt
+        for p in params:
+            p.grad = None
+        torch.manual_seed(99)
+        outs.append((step(x.clone().requires_grad_(True)), [p.grad.clone() for p in params]))
+    assert torch.equal(outs[0][0], outs[1][0])
+    for a, b in zip(outs[0][1], outs[1][1]):
+        assert rel_linf(a, b) < 1e-4          # (fp32 atomics of the prompt / bias-table gradients land in a different order)

@@ -8,10 +8,11 @@ from . import _lib
 from .geometry import Geometry, get_geometry
 from . import functional
 from . import graphs
+from . import trainer
 from .graphs import GraphedStep
 from .modules import (ConsecutiveSwinBlocks, SwinTransformerBlock, PatchMerging, WindowAttention, RelativePE,
                       BiasTables, window_partition, window_reverse, get_attn_mask, SwinUnetR, SwinUnetRConfig, SwinUpBlock)
 
 __all__ = ['ConsecutiveSwinBlocks', 'SwinTransformerBlock', 'PatchMerging', 'WindowAttention', 'RelativePE',
            'BiasTables', 'window_partition', 'window_reverse', 'get_attn_mask', 'Geometry', 'get_geometry',
-           'functional', 'graphs', 'GraphedStep', 'SwinUnetR', 'SwinUnetRConfig', 'SwinUpBlock']
+           'functional', 'graphs', 'trainer', 'GraphedStep', 'SwinUnetR', 'SwinUnetRConfig', 'SwinUpBlock']

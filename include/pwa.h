@@ -121,6 +121,12 @@ int pwa_colsum_f32(const float* src, float* dst, int S, int64_t n, void* stream)
  * x == y is allowed; both 16-byte aligned. */
 int pwa_dropout(const void* x, void* y, int64_t n, float p_drop, const void* seed_dev, int dtype, void* stream);
 
+/* pwa_dropout over a [rows][C] tensor (C % 4 == 0, C <= 1024) that also emits colsum[c] = sum_rows y[r][c] (fp32 [C] on the
+ * DEVICE, zeroed by this call).  Backward use: y = gradient of the Linear output in front of the dropout, colsum = gradient
+ * of that Linear's bias (attn.proj.bias, window_attention.py:32,60) without a separate reduction pass. */
+int pwa_dropout_colsum(const void* x, void* y, int64_t rows, int C, float p_drop, const void* seed_dev, float* colsum,
+                       int dtype, void* stream);
+
 /* ---- (b) fused prompted window attention, forward -------------------------------------------- */
 
 typedef struct pwa_attn_shape {

@@ -615,8 +615,11 @@ def new_dropout_seed(device, words: int = 2) -> torch.Tensor:
 
 class _SeededDropout(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, p_drop, seed):
+    def forward(ctx, x, p_drop, seed, bias_of_x=None):
+        # bias_of_x: the bias parameter of the Linear that produced x -- its gradient (column sums of dx) comes out of
+        # the backward's masking pass (pwa_dropout_colsum); that Linear is then called with bias_grad=False
         x = x.contiguous()
+        ctx.bias_dtype = None if bias_of_x is None else bias_of_x.dtype
         y = torch.empty_like(x)
         with torch.cuda.device(x.device), _timed("dropout", 1, 2.0 * x.numel() * x.element_size(), x):
             rc = _lib.lib.pwa_dropout(_ptr(x), _ptr(y), x.numel(), float(p_drop), _ptr(seed), _dtype_code(x), _stream(x))
@@ -630,13 +633,24 @@ class _SeededDropout(torch.autograd.Function):
         (seed,) = ctx.saved_tensors
         dy = dy.contiguous()
         dx = torch.empty_like(dy)
+        Cc = dy.shape[-1]
+        db = None
         with torch.cuda.device(dy.device), _timed("dropout", 1, 2.0 * dy.numel() * dy.element_size(), dy):
-            rc = _lib.lib.pwa_dropout(_ptr(dy), _ptr(dx), dy.numel(), ctx.p_drop, _ptr(seed), _dtype_code(dy), _stream(dy))
+            if ctx.bias_dtype is not None:
+                db = torch.empty(Cc, dtype=torch.float32, device=dy.device)
+                rc = _lib.lib.pwa_dropout_colsum(_ptr(dy), _ptr(dx), dy.numel() // Cc, Cc, ctx.p_drop, _ptr(seed), _ptr(db),
+                                                 _dtype_code(dy), _stream(dy))
+            else:
+                rc = _lib.lib.pwa_dropout(_ptr(dy), _ptr(dx), dy.numel(), ctx.p_drop, _ptr(seed), _dtype_code(dy), _stream(dy))
         _lib.check(rc, "pwa_dropout")
-        return dx, None, None
+        return dx, None, None, (None if db is None else db.to(ctx.bias_dtype))
 
 
-def seeded_dropout(x: torch.Tensor, p_drop: float, seed: Optional[torch.Tensor] = None) -> torch.Tensor:
+def dropout_colsum_supported(C: int) -> bool:
+    return C % 4 == 0 and C <= 1024
+
+
+def seeded_dropout(x: torch.Tensor, p_drop: float, seed: Optional[torch.Tensor] = None, bias_of_x=None) -> torch.Tensor:
     """Dropout whose mask is a pure function of two device seed words and the element index (csrc/dropout.cu): the
     reference's nn.Dropout(proj_drop) (window_attention.py:60), safe under activation checkpointing inside a CUDA graph."""
     _require_cuda(x, seed)
@@ -646,7 +660,7 @@ def seeded_dropout(x: torch.Tensor, p_drop: float, seed: Optional[torch.Tensor] 
         seed = new_dropout_seed(x.device)
     if seed.dtype != torch.int32 or seed.numel() < 2:
         raise ValueError("seeded_dropout: seed must be an int32 tensor with two words")
-    return _SeededDropout.apply(x, float(p_drop), seed)
+    return _SeededDropout.apply(x, float(p_drop), seed, bias_of_x)
 
 
 def prompted_window_attention_packed(qkv, kvp, th, tw, td, tok, ids, heads: int, ws: Sequence[int], scale: float,

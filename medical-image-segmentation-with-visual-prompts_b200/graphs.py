@@ -90,12 +90,18 @@ class GraphedStep:
             p.grad = g
 
     def allreduce_flat(self, group=None):
-        """Average the flat gradient buffer over the data-parallel group: one NCCL all-reduce, one scale kernel."""
+        """Average the flat gradient buffer over the data-parallel group: ONE NCCL all-reduce with the 1/world scale folded
+        into the reduction (ReduceOp.AVG; gloo has no AVG: sum + scale there).
+        (Capturing bucketed all-reduces INSIDE the step's graph, on a branch parallel to the backward, was tried in round 2:
+        the 2-GPU run hung under capture and was dropped -- the exchange stays one launch after the replay.)"""
         import torch.distributed as dist
         world = dist.get_world_size(group)
         if world > 1:
-            dist.all_reduce(self.flat_grad, group=group)
-            self.flat_grad.div_(world)
+            if dist.get_backend(group) == "nccl":
+                dist.all_reduce(self.flat_grad, op=dist.ReduceOp.AVG, group=group)
+            else:
+                dist.all_reduce(self.flat_grad, group=group)
+                self.flat_grad.div_(world)
 
     @property
     def input_grads(self):

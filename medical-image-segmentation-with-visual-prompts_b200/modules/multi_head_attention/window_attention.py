@@ -93,8 +93,10 @@ class WindowAttention(nn.Module):
                 vp = PF.multi_linear(prompts, None, self.to_v.weight)
             o = PF.prompted_window_attention(qq, kk, vv, kp, vp, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok,
                                              mask, self.num_heads, pos_bias.ws, self.scale, impl, p_drop=p_drop, seed=drop_seed)
-        o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'), bias_grad=proj_bias_grad,
-                            lowp_bias=(lowp or {}).get('proj_b'))
+        # with projection dropout the gradient of proj.bias is a by-product of the dropout's backward pass
+        drop_db = p_proj > 0 and proj_bias_grad and PF.dropout_colsum_supported(o.shape[-1])
+        o = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=(lowp or {}).get('proj'),
+                            bias_grad=proj_bias_grad and not drop_db, lowp_bias=(lowp or {}).get('proj_b'))
         # projection dropout (reference :60): seeded kernel instead of nn.Dropout, so that a checkpointed block inside a
         # CUDA graph recomputes the same mask without touching the generator state (csrc/dropout.cu)
-        return PF.seeded_dropout(o, p_proj, proj_seed) if p_proj > 0 else o
+        return PF.seeded_dropout(o, p_proj, proj_seed, bias_of_x=self.proj.bias if drop_db else None) if p_proj > 0 else o

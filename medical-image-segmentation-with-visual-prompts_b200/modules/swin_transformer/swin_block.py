@@ -245,14 +245,14 @@ class SwinTransformerBlock(nn.Module):
         if fused_ln:
             # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway
             # (d of the attention branch, and d of y which equals d of m: both only meet in y + m); the two Linears
-            # skip their own bias reductions.  Only valid without projection dropout between proj and the add.
+            # skip their own bias reductions.  mlp.bias: always.  proj.bias: only without projection dropout between proj
+            # and the add (with it, d(proj output) = mask * d(attention branch), a different column sum).
             fuse_db = not (self.training and self.attn.proj_drop.p > 0)
             a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
                           prompt_kv=side.kvp, lowp=lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
             y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
-                                     bias_of_x=self.attn.proj.bias if fuse_db else None,
-                                     bias_of_res=self.mlp.bias if fuse_db else None)
-            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=not fuse_db,
+                                     bias_of_x=self.attn.proj.bias if fuse_db else None, bias_of_res=self.mlp.bias)
+            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=False,
                                 lowp_bias=lowp['mlp_b'])
             return y, m
         y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,

@@ -754,6 +754,24 @@ def test_seeded_projection_dropout_matches_oracle_mask(dtype, n):
     assert rel_linf(x.grad, (g.double() * keep).to(dtype)) < (1e-6 if dtype == torch.float32 else 4e-3)
 
 
+@pytest.mark.parametrize("C", [12, 48, 96, 192, 768])
+def test_dropout_backward_emits_bias_gradient(C):
+    """pwa_dropout_colsum: the masked gradient AND its column sums (= the gradient of the bias of the Linear in front of the
+    dropout) in one pass, against torch."""
+    torch.manual_seed(C)
+    rows = 1000 + C
+    lin = torch.nn.Linear(C, C).to(DEV)
+    x = torch.randn(rows, C, device=DEV).bfloat16()
+    seed = torch.tensor([5, 6], dtype=torch.int32, device=DEV)
+    o = PF.multi_linear(x, lin.bias, lin.weight, bias_grad=False)
+    y = PF.seeded_dropout(o, 0.1, seed, bias_of_x=lin.bias)
+    g = torch.randn(rows, C, device=DEV).bfloat16()
+    y.backward(g)
+    keep = R.elementwise_dropout_keep_factor([5, 6], rows * C, 0.1).to(DEV).reshape(rows, C)
+    ref = (g.double() * keep).sum(0)                 # (the kernel sums the fp32 products, before the bf16 rounding of dx)
+    assert rel_linf(lin.bias.grad, ref) < 1e-5
+
+
 def test_reference_training_config_inside_a_cuda_graph():
     """configurations/example_configs.yml:17-19 (use_checkpoint, attn_drop = proj_drop = 0.1) captured into ONE CUDA
     graph: the recomputation must see the forward's masks (seed words drawn outside the checkpointed region), every

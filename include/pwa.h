@@ -219,6 +219,21 @@ int pwa_ln_bwd2(const void* dy, const void* x, const float* gamma, const float* 
                 const void* dres, void* dx, float* dgamma, float* dbeta, float* dres_colsum, float* dx_colsum,
                 int64_t rows, int C, int dtype, void* stream);
 
+/* ---- token-domain GEMM with fused LayerNorm / residual / dropout prologue (tcgen05, bf16) ------------------------------- */
+
+/* s = dropout(x) (+ res) ; z = LayerNorm(s) * gamma + beta (gamma == NULL: z = s) ; y = z @ W^T (+ bias).
+ * x, res, sum_out, ln_out [T][C] bf16; W [Cout][C] bf16 row-major; bias [Cout] bf16 or NULL; y [T][Cout] bf16; mean, rstd fp32
+ * [T] or NULL.  sum_out (s) and ln_out (z) are written when non-NULL.  p_drop > 0: the mask of pwa_dropout for the same seed
+ * words (element index = row * C + column), so pwa_dropout / pwa_dropout_colsum on the upstream gradient is its backward.
+ * One pass over the tokens for what the reference runs as LayerNorm + Linear (+ Dropout + add) modules: swin_block.py:216 +
+ * window_attention.py:42-44 (attn_norm + to_q|to_k|to_v as one [C -> 3C] projection), window_attention.py:60 +
+ * swin_block.py:222-227 (proj_drop, residual add, mlp_norm, the single-Linear MLP).  C % 16 == 0, 16 <= C <= 192,
+ * Cout % 16 == 0 (pwa_token_gemm_supported). */
+int pwa_token_gemm_supported(int C, int Cout);
+int pwa_token_gemm_fwd(const void* x, const void* res, const float* gamma, const float* beta, const void* W, const void* bias,
+                       void* sum_out, void* ln_out, void* y, float* mean, float* rstd, int64_t T, int C, int Cout, float eps,
+                       float p_drop, const void* seed_dev, void* stream);
+
 /* 1 iff the bf16 tcgen05 kernel supports this shape (else impl=0 falls back to the fp32-math kernel). */
 int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype);
 

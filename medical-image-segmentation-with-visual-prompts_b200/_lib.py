@@ -63,6 +63,10 @@ def _load():
     lib.pwa_dropout.restype = i32
     lib.pwa_dropout_colsum.argtypes = [vp, vp, C.c_int64, i32, C.c_float, vp, vp, i32, vp]
     lib.pwa_dropout_colsum.restype = i32
+    lib.pwa_token_gemm_supported.argtypes = [i32, i32]
+    lib.pwa_token_gemm_supported.restype = i32
+    lib.pwa_token_gemm_fwd.argtypes = [vp] * 11 + [C.c_int64, i32, i32, C.c_float, C.c_float, vp, vp]
+    lib.pwa_token_gemm_fwd.restype = i32
     if hasattr(lib, "pwa_debug_fwd_timeline"):          # debug builds only (make TIMELINE=1, include/pwa_debug.h)
         lib.pwa_debug_fwd_timeline.argtypes = [vp, i32]
         lib.pwa_debug_fwd_timeline.restype = i32
@@ -87,7 +91,7 @@ def _load():
 lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map", "pwa_attn_sel_table",
-                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_dropout", "pwa_dropout_colsum", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
+                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_dropout", "pwa_dropout_colsum", "pwa_token_gemm_supported", "pwa_token_gemm_fwd", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
                     "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 

@@ -771,3 +771,150 @@ def multi_linear(x, bias, *weights, lowp=None, bias_grad=True, lowp_bias=None):
     """bias_grad=False: the bias gradient is produced elsewhere (add_layer_norm's fused column sums); lowp / lowp_bias:
     the weights (concatenated) and the bias already cast to x.dtype."""
     return _MultiLinear.apply(x, bias, lowp, bias_grad, lowp_bias, *weights)
+
+
+# ------------------------------------------------------------------------------------------------
+# token-domain GEMMs with fused LayerNorm / residual / dropout prologue (csrc/token_gemm.cu, tcgen05)
+# ------------------------------------------------------------------------------------------------
+def token_gemm_supported(C: int, Cout: int, dtype) -> bool:
+    return dtype == torch.bfloat16 and bool(_lib.lib.pwa_token_gemm_supported(int(C), int(Cout)))
+
+
+def token_gemm_profitable(C: int, rows: int) -> bool:
+    """Where the fused kernel beats separate LayerNorm kernels + cuBLAS today (tools/bench_token_gemm.py): the narrow,
+    token-rich stages (C = 48: 442 K tokens at 96^3).  At C >= 96 its tile phases run serially on one CTA per SM and the
+    separate kernels win; those stages keep them."""
+    return C <= 48 and rows >= 32768
+
+
+def _token_gemm_raw(x2, res2, g32, b32, w, bias, want_sum, want_ln, want_stats, eps, p_drop, seed):
+    rows, Cc = x2.shape
+    Cout = w.shape[0]
+    dev = x2.device
+    y = torch.empty((rows, Cout), dtype=x2.dtype, device=dev)
+    s = torch.empty_like(x2) if want_sum else None
+    z = torch.empty_like(x2) if want_ln else None
+    mean = torch.empty(rows, dtype=torch.float32, device=dev) if want_stats else None
+    rstd = torch.empty(rows, dtype=torch.float32, device=dev) if want_stats else None
+    nbytes = ((1 if res2 is None else 2) + (1 if want_sum else 0) + (1 if want_ln else 0)) * x2.numel() * 2 + y.numel() * 2
+    with torch.cuda.device(dev), _timed("token_gemm", 1, float(nbytes), x2):
+        rc = _lib.lib.pwa_token_gemm_fwd(_ptr(x2), _ptr(res2), _ptr(g32), _ptr(b32), _ptr(w), _ptr(bias), _ptr(s), _ptr(z), _ptr(y),
+                                         _ptr(mean), _ptr(rstd), rows, Cc, Cout, float(eps), float(p_drop), _ptr(seed), _stream(x2))
+    _lib.check(rc, "pwa_token_gemm_fwd")
+    return y, s, z, mean, rstd
+
+
+def _ln_backward_raw(dy, x, g32, mean, rstd, dres, want_res_colsum, want_x_colsum):
+    Cc = x.shape[-1]
+    rows = x.numel() // Cc
+    dx = torch.empty_like(x)
+    f32 = dict(dtype=torch.float32, device=x.device)
+    dg, db = torch.empty(Cc, **f32), torch.empty(Cc, **f32)
+    dbr = torch.empty(Cc, **f32) if want_res_colsum and dres is not None else None
+    dbx = torch.empty(Cc, **f32) if want_x_colsum else None
+    nbytes = (3 if dres is None else 4) * x.numel() * x.element_size()
+    with torch.cuda.device(x.device), _timed("ln_bwd", 1, float(nbytes), x):
+        rc = _lib.lib.pwa_ln_bwd2(_ptr(dy), _ptr(x), _ptr(g32), _ptr(mean), _ptr(rstd), _ptr(dres), _ptr(dx), _ptr(dg), _ptr(db),
+                                  _ptr(dbr), _ptr(dbx), rows, Cc, _dtype_code(x), _stream(x))
+    _lib.check(rc, "pwa_ln_bwd")
+    return dx, dg, db, dbr, dbx
+
+
+class _LnLinearPass(torch.autograd.Function):
+    """(x_alias, y) with y = LayerNorm(x) @ cat(weights)^T in ONE kernel (attn_norm + to_q|to_k|to_v, swin_block.py:216 +
+    window_attention.py:42-44); x_alias = x for the block's shortcut, whose gradient the LayerNorm backward sums in."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, lowp_w, *weights):
+        x = x.contiguous()
+        Cc = x.shape[-1]
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        w = lowp_w if lowp_w is not None else (weights[0] if len(weights) == 1 else torch.cat(weights, dim=0)).detach().to(x.dtype)
+        w = w.contiguous()
+        y, _, tokens, mean, rstd = _token_gemm_raw(x.view(-1, Cc), None, g32, b32, w, None, False, True, True, eps, 0.0, None)
+        ctx.save_for_backward(x, g32, mean, rstd, tokens, w)
+        ctx.meta = ([wt.shape[0] for wt in weights], [wt.dtype for wt in weights], (gamma.dtype, beta.dtype))
+        return x.view_as(x), y.view(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, dalias, dy):
+        x, g32, mean, rstd, tokens, w = ctx.saved_tensors
+        rows_w, wdts, (gd, bd) = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        dtok = torch.mm(dy2, w)
+        dws = [None] * len(rows_w)
+        if any(ctx.needs_input_grad[5:]):
+            dw = _wgrad(dy2.contiguous(), tokens)
+            o = 0
+            for i, r in enumerate(rows_w):
+                if ctx.needs_input_grad[5 + i]:
+                    dws[i] = dw[o:o + r].to(wdts[i])
+                o += r
+        dres = dalias.contiguous().view(-1, x.shape[-1]) if dalias is not None else None
+        dx, dg, db, _, _ = _ln_backward_raw(dtok, x.view(-1, x.shape[-1]), g32, mean, rstd, dres, False, False)
+        return (dx.view_as(x), dg.to(gd), db.to(bd), None, None, *dws)
+
+
+def ln_linear_pass(x, gamma, beta, eps, lowp_w, *weights):
+    _require_cuda(x, gamma, beta, lowp_w)
+    return _LnLinearPass.apply(x, gamma, beta, eps, lowp_w, *weights)
+
+
+class _DropAddLnLinear(torch.autograd.Function):
+    """(s, m) with s = dropout(a) + res and m = LayerNorm(s) @ W^T + bias in ONE kernel: projection dropout, the residual add,
+    mlp_norm and the single-Linear MLP of the block (window_attention.py:60, swin_block.py:222-227).  `bias_of_a` is the
+    bias of the Linear that produced `a` (attn.proj.bias): its gradient is the column sum of d(a), a by-product of the
+    backward passes here, as is the gradient of `bias` (column sum of the gradient that reaches s directly)."""
+
+    @staticmethod
+    def forward(ctx, a, res, gamma, beta, eps, lowp_w, lowp_b, p_drop, seed, weight, bias, bias_of_a):
+        a, res = a.contiguous(), res.contiguous()
+        Cc = a.shape[-1]
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        w = (lowp_w if lowp_w is not None else weight.detach().to(a.dtype)).contiguous()
+        bb = (lowp_b if lowp_b is not None else bias.detach().to(a.dtype)).contiguous() if bias is not None else None
+        m, s, z, mean, rstd = _token_gemm_raw(a.view(-1, Cc), res.view(-1, Cc), g32, b32, w, bb, True, True, True, eps, p_drop, seed)
+        ctx.save_for_backward(s, g32, mean, rstd, z, w, seed)
+        ctx.meta = (float(p_drop), weight.dtype, None if bias is None else bias.dtype, None if bias_of_a is None else bias_of_a.dtype,
+                    (gamma.dtype, beta.dtype), a.shape)
+        return s.view_as(a), m.view(*a.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, ds, dm):
+        s, g32, mean, rstd, z, w, seed = ctx.saved_tensors
+        p_drop, wdt, bdt, badt, (gd, bd), ashape = ctx.meta
+        Cc = s.shape[-1]
+        dm2 = dm.reshape(-1, dm.shape[-1]).contiguous()
+        dz = torch.mm(dm2, w)
+        dw = _wgrad(dm2, z).to(wdt) if ctx.needs_input_grad[9] else None
+        ds2 = ds.contiguous().view(-1, Cc) if ds is not None else None
+        want_b = bdt is not None and ctx.needs_input_grad[10] and ds2 is not None
+        want_ba = badt is not None and ctx.needs_input_grad[11]
+        dx, dg, db, dbr, dbx = _ln_backward_raw(dz, s, g32, mean, rstd, ds2, want_b, want_ba and p_drop == 0.0)
+        dbias = dbr.to(bdt) if dbr is not None else (dm2.sum(dim=0, dtype=torch.float32).to(bdt) if bdt is not None and ctx.needs_input_grad[10] else None)
+        if p_drop > 0.0:
+            da = torch.empty_like(dx)
+            dba = None
+            with torch.cuda.device(dx.device), _timed("dropout", 1, 2.0 * dx.numel() * dx.element_size(), dx):
+                if want_ba and dropout_colsum_supported(Cc):
+                    dba = torch.empty(Cc, dtype=torch.float32, device=dx.device)
+                    rc = _lib.lib.pwa_dropout_colsum(_ptr(dx), _ptr(da), dx.numel() // Cc, Cc, p_drop, _ptr(seed), _ptr(dba),
+                                                     _dtype_code(dx), _stream(dx))
+                else:
+                    rc = _lib.lib.pwa_dropout(_ptr(dx), _ptr(da), dx.numel(), p_drop, _ptr(seed), _dtype_code(dx), _stream(dx))
+            _lib.check(rc, "pwa_dropout")
+            if want_ba and dba is None:
+                dba = da.sum(dim=0, dtype=torch.float32)
+        else:
+            da, dba = dx, dbx
+        return (da.view(ashape), dx.view(ashape), dg.to(gd), db.to(bd), None, None, None, None, None, dw, dbias,
+                None if dba is None else dba.to(badt))
+
+
+def drop_add_ln_linear(a, res, gamma, beta, eps, lowp_w, lowp_b, p_drop, seed, weight, bias, bias_of_a=None):
+    _require_cuda(a, res, gamma, beta, weight, seed)
+    if a.shape != res.shape or a.dtype != res.dtype:
+        raise ValueError("drop_add_ln_linear: a and res must match")
+    if p_drop > 0 and seed is None:
+        seed = new_dropout_seed(a.device)
+    return _DropAddLnLinear.apply(a, res, gamma, beta, eps, lowp_w, lowp_b, float(p_drop), seed, weight, bias, bias_of_a)

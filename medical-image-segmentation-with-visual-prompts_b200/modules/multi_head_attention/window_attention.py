@@ -49,6 +49,22 @@ class WindowAttention(nn.Module):
             return None
         return PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight, lowp=(lowp or {}).get('kv'))
 
+    def forward_packed(self, qkv: torch.Tensor, pos_bias: BiasTables, mask, prompt_kv, lowp: dict, drop_seed=None):
+        """Self-attention from an already projected q|k|v [B,P,N,3C] (the block's fused LayerNorm + projection kernel):
+        attention + output projection with its bias, WITHOUT the projection dropout -- returns (a, p_proj, proj_seed) for
+        the block's fused dropout + residual + mlp_norm + MLP kernel, whose backward also yields proj.bias's gradient."""
+        p_drop = float(self.attn_drop.p) if self.training else 0.0
+        p_proj = float(self.proj_drop.p) if self.training else 0.0
+        if (p_drop > 0 or p_proj > 0) and drop_seed is None:
+            drop_seed = PF.new_dropout_seed(qkv.device, 4)
+        attn_seed = proj_seed = None
+        if drop_seed is not None:
+            attn_seed, proj_seed = drop_seed[:2], drop_seed[2:4]
+        o = PF.prompted_window_attention_packed(qkv, prompt_kv, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
+                                                self.num_heads, pos_bias.ws, self.scale, self.impl, p_drop=p_drop, seed=attn_seed)
+        a = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=lowp.get('proj'), bias_grad=False, lowp_bias=lowp.get('proj_b'))
+        return a, p_proj, proj_seed
+
     def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias: Optional[BiasTables] = None,
                 mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None, lowp: Optional[dict] = None,
                 proj_bias_grad: bool = True, drop_seed: Optional[torch.Tensor] = None,

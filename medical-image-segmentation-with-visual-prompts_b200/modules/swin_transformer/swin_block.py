@@ -31,6 +31,11 @@ from ..multi_head_attention import BiasTables, RelativePE, WindowAttention
 from .down import PatchMerging
 
 
+import os as _os
+_NO_TOKEN_GEMM = _os.environ.get("PWA_NO_TOKEN_GEMM", "0") == "1"      # (A/B measurements: separate LayerNorm kernels + cuBLAS)
+_FORCE_TOKEN_GEMM = _os.environ.get("PWA_FORCE_TOKEN_GEMM", "0") == "1"  # (tests: the fused kernels at every supported shape)
+
+
 def _is_channels_last(x):
     """[B,C,H,W,D] tensor whose memory is [B,H,W,D,C]-contiguous (what PatchMerging's final rearrange leaves,
     reference down.py:48-53)."""
@@ -231,6 +236,19 @@ class SwinTransformerBlock(nn.Module):
         if side is None:
             side = self._side_inputs(p, cdt, c)
         fused_ln = PF.layer_norm_supported(c)
+        if (fused_ln and PF.token_gemm_supported(c, 3 * c, xw.dtype) and not _NO_TOKEN_GEMM
+                and (_FORCE_TOKEN_GEMM or PF.token_gemm_profitable(c, xw.numel() // c))):
+            # LayerNorm-1 + q|k|v projection in ONE tcgen05 kernel, and projection dropout + residual add +
+            # LayerNorm-2 + MLP Linear in ONE kernel (csrc/token_gemm.cu); the attention output projection stays a GEMM
+            a_ = self.attn
+            if side.ready is not None:
+                torch.cuda.current_stream(xw.device).wait_event(side.ready)
+            xw, qkv = PF.ln_linear_pass(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6, side.lowp['qkv'],
+                                        a_.to_q.weight, a_.to_k.weight, a_.to_v.weight)
+            th, tw, td, tok = side.tables
+            a, p_proj, proj_seed = a_.forward_packed(qkv, BiasTables(th, tw, td, tok, ws), ids, side.kvp, side.lowp, drop_seed)
+            return PF.drop_add_ln_linear(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6, side.lowp['mlp'], side.lowp['mlp_b'],
+                                         p_proj, proj_seed, self.mlp.weight, self.mlp.bias, bias_of_a=a_.proj.bias)
         if fused_ln:
             # pwa LayerNorm kernels (csrc/ln.cu); the `+ shortcut` of :222 is fused into mlp_norm
             # (xw is needed again as the shortcut: its second use goes through the alias, so that both of its gradients

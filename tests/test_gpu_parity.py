@@ -810,3 +810,74 @@ def test_reference_training_config_inside_a_cuda_graph():
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
         assert rel_linf(a, b) < 1e-4          # (fp32 atomics of the prompt / bias-table gradients land in a different order)
+
+
+@pytest.mark.parametrize("C,Cout", [(48, 144), (48, 48), (96, 288), (192, 576), (192, 192), (16, 48)])
+@pytest.mark.parametrize("mode", ["ln", "res_ln_bias", "drop_res_ln_bias", "plain_bias"])
+def test_token_gemm_kernel_vs_float64(C, Cout, mode):
+    """csrc/token_gemm.cu: s = dropout(x) + res, z = LayerNorm(s), y = z @ W^T + bias in one tcgen05 kernel,
+    against float64 torch on the same bf16 inputs (with the kernel's own roundings of s and z restated), ragged row count."""
+    torch.manual_seed(C * 7 + Cout)
+    rows = 128 * 9 + 37
+    x = torch.randn(rows, C, device=DEV).bfloat16()
+    res = torch.randn(rows, C, device=DEV).bfloat16() if "res" in mode else None
+    W = (torch.randn(Cout, C, device=DEV) / C ** 0.5).bfloat16()
+    bias = (0.1 * torch.randn(Cout, device=DEV)).bfloat16() if "bias" in mode else None
+    ln = "ln" in mode
+    gamma = (1 + 0.2 * torch.randn(C, device=DEV)) if ln else None
+    beta = 0.1 * torch.randn(C, device=DEV) if ln else None
+    p_drop = 0.1 if "drop" in mode else 0.0
+    words = [77, 88]
+    seed = torch.tensor(words, dtype=torch.int32, device=DEV) if p_drop else None
+    y, s, z, mean, rstd = PF._token_gemm_raw(x, res, gamma, beta, W, bias, res is not None or p_drop > 0, ln, ln, 1e-6, p_drop, seed)
+    s64 = x.double()
+    if p_drop:
+        keep = R.elementwise_dropout_keep_factor(words, rows * C, p_drop).to(DEV).reshape(rows, C)
+        s64 = (s64 * keep).to(torch.bfloat16).double()
+    if res is not None:
+        s64 = (s64 + res.double()).to(torch.bfloat16).double()
+    if s is not None:
+        assert torch.equal(s.double(), s64)                        # bit-exact: one fp32 add, one rounding
+    z64 = s64
+    if ln:
+        m64 = s64.mean(dim=1, keepdim=True)
+        r64 = (s64.var(dim=1, unbiased=False, keepdim=True) + 1e-6).rsqrt()
+        z64 = (s64 - m64) * r64 * gamma.double() + beta.double()
+        assert rel_linf(mean, m64.squeeze(1)) < 1e-5 and rel_linf(rstd, r64.squeeze(1)) < 1e-5
+        assert rel_linf(z, z64) < 6e-3
+        z64 = z.double()                                           # the GEMM consumes the stored bf16 z
+    y64 = z64 @ W.double().t() + (bias.double() if bias is not None else 0.0)
+    assert rel_linf(y, y64) < 6e-3
+
+
+def test_block_with_fused_token_gemms_matches_separate_kernels():
+    """The block on the fused token-GEMM kernels (default) against the same block on separate LayerNorm kernels + cuBLAS
+    (PWA_NO_TOKEN_GEMM path): forward and every gradient, with and without dropout (same seeds)."""
+    import importlib
+    sb = importlib.import_module(pwa_b200.SwinTransformerBlock.__module__)
+    torch.manual_seed(21)
+    for drop in (0.0, 0.1):
+        blk = pwa_b200.SwinTransformerBlock(hidden_channels=48, window_size=(8, 8, 4), pos_bias_embed_dim=64, num_heads=4,
+                                            max_prompts=1, tokens_per_prompt=64, shift_size=(4, 4, 2), attn_drop=drop,
+                                            proj_drop=drop).to(DEV).train()
+        x = torch.randn(2, 48, 16, 16, 8, device=DEV).bfloat16()
+        p = (0.2 * torch.randn(2, 64, 48, device=DEV)).bfloat16()
+        res = []
+        for off in (False, True):
+            sb._NO_TOKEN_GEMM = off
+            try:
+                for prm in blk.parameters():
+                    prm.grad = None
+                xg, pg = x.clone().requires_grad_(True), p.clone().requires_grad_(True)
+                torch.manual_seed(5)
+                y = blk(xg, pg)
+                y.float().square().mean().backward()
+                res.append((y.detach(), xg.grad, pg.grad, [q.grad.clone() for q in blk.parameters()]))
+            finally:
+                sb._NO_TOKEN_GEMM = False
+        assert rel_linf(res[0][0], res[1][0]) < 1e-2
+        assert rel_linf(res[0][1], res[1][1]) < 2e-2 and rel_linf(res[0][2], res[1][2]) < 2e-2
+        gmax = max(g.abs().max().item() for g in res[1][3])
+        for (n, _), a, b in zip(blk.named_parameters(), res[0][3], res[1][3]):
+            den = max(b.abs().max().item(), 1e-3 * gmax)
+            assert (a - b).abs().max().item() / den < 2e-2, n

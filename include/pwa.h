@@ -114,6 +114,12 @@ int pwa_gather_rows(const void* src_a, const void* src_b, void* dst, const int32
  * torch autograd in the reference): dW = dy^T x is computed as S batched slices of the token axis with fp32 partials. */
 int pwa_colsum_f32(const float* src, float* dst, int S, int64_t n, void* stream);
 
+/* dst[c] = sum over r < rows of x[r][c]: x [rows][C] bf16 or fp32 (dtype = PWA_BF16 / PWA_F32), dst [C] fp32, both on the
+ * DEVICE; dst is zeroed by the call.  The bias gradient of the q|k|v projection (window_attention.py:28-30: nn.Linear with
+ * bias; torch autograd sums the packed dq|dk|dv rows over all tokens there).  C must be a multiple of the elements per
+ * 16 bytes (8 / 4) and at most 512 such vectors; x 16-byte aligned.  fp32 atomics: the sum order is not fixed. */
+int pwa_colsum_rows(const void* x, float* dst, int64_t rows, int C, int dtype, void* stream);
+
 /* y[i] = keep(i) ? x[i] / keep_rate : 0 for i < n, keep(i) a counter-based hash of the two uint32 words at seed_dev (DEVICE
  * memory) and i; rate in steps of 1/256.  Replaces nn.Dropout(proj_drop) after the attention output projection
  * (window_attention.py:33,60).  The same call on dy is the backward.  No generator state is involved, so an activation-

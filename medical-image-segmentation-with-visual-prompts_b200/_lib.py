@@ -59,6 +59,8 @@ def _load():
     lib.pwa_gather_rows.restype = i32
     lib.pwa_colsum_f32.argtypes = [f32p, f32p, i32, C.c_int64, vp]
     lib.pwa_colsum_f32.restype = i32
+    lib.pwa_colsum_rows.argtypes = [vp, f32p, C.c_int64, i32, i32, vp]
+    lib.pwa_colsum_rows.restype = i32
     lib.pwa_dropout.argtypes = [vp, vp, C.c_int64, C.c_float, vp, i32, vp]
     lib.pwa_dropout.restype = i32
     lib.pwa_dropout_colsum.argtypes = [vp, vp, C.c_int64, i32, C.c_float, vp, vp, i32, vp]
@@ -91,7 +93,7 @@ def _load():
 lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map", "pwa_attn_sel_table",
-                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_dropout", "pwa_dropout_colsum", "pwa_token_gemm_supported", "pwa_token_gemm_fwd", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
+                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_colsum_rows", "pwa_dropout", "pwa_dropout_colsum", "pwa_token_gemm_supported", "pwa_token_gemm_fwd", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
                     "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 

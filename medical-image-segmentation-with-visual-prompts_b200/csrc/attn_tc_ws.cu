@@ -1,19 +1,25 @@
 // (b) fused prompted window attention forward, warp-specialised (tcgen05 + TMEM, bf16 I/O) -- round-2 kernel.
 //
-// One persistent CTA per SM (512 threads) = one fixed head, walking (sample, window) pairs.  The softmax of this path
-// is bound by the MUFU pipe (one ex2 per logit, 16 / clk / SM), so everything else is taken off the threads that
-// compute exponentials and hidden behind them with mbarrier hand-offs:
-//     warps 0-3 / 4-7   softmax group 0 / 1: query tile 0 / 1 (128 rows = 128 TMEM lanes) of the current window.  Per UNIT
-//                       of 64 keys: wait for S, tcgen05.ld -> exp2 (FFMA2 + MUFU + pack) -> shift mask (one PRMT per
-//                       packed pair) -> dropout (one AND per pair) -> tcgen05.st of the bf16 probabilities over the
-//                       consumed S columns; per window: drain O, normalise, write the output rows and the log-sum-exp.
-//     warps 8-11        staging: the NEXT window's Q / K / [V | 1] head slices global -> registers -> UMMA canonical
-//                       shared-memory layouts (double-buffered operand sets), |q|^2 per row and max |k|^2 (stabiliser),
-//                       region ids + PRMT selector table; also fetches the next window index (per-head work counter).
-//     warp 12 / 13      MMA issuer of group 0 / 1 (one lane): S = Q'.K'^T of unit n + 2 is issued while the group still
-//                       works on unit n (three S buffers per group in TMEM), O += P.[V | 1] as soon as a unit's P is
-//                       stored.  A thread's tcgen05.mma instructions execute in issue order, so S(n + 3) may overwrite the
-//                       buffer whose P fed PV(n) without a further barrier.
+// One persistent CTA per SM (768 threads = 24 warps, 6 per scheduler) = one fixed head, walking (sample, window) pairs.
+// The softmax of this path is bound by the MUFU pipe (one ex2 per logit, 16 / clk / SM), so everything else is taken off
+// the threads that compute exponentials and hidden behind them with mbarrier hand-offs:
+//     warps 0-15        softmax: group = warp / 8 owns query tile 0 / 1 (128 rows = 128 TMEM lanes) of the current window,
+//                       set = (warp / 4) % 2 takes alternate UNITS of 64 keys of the group's stream, lane quadrant = warp % 4.
+//                       Per unit: wait for S, tcgen05.ld -> exp2 (FFMA2 + MUFU + pack) -> shift mask (one PRMT per packed
+//                       pair) -> dropout (one AND per pair) -> tcgen05.st of the bf16 probabilities over the consumed S
+//                       columns; per window: drain O, normalise, write the output rows and the log-sum-exp.
+//     warps 16 / 17     MMA issuer of group 0 / 1 (warp-uniform loop, elect.sync picks the issuing lane so that descriptors
+//                       stay in uniform registers): S = Q'.K'^T of unit n + 2 is issued while the group still works on
+//                       unit n (three S buffers per group in TMEM), O += P.[V | 1] as soon as a unit's P is stored.  A
+//                       thread's tcgen05.mma instructions execute in issue order, so S(n + 3) may overwrite the buffer
+//                       whose P fed PV(n) without a further barrier.  The next window is opened with a NON-blocking
+//                       try_wait on its operand barrier, so PV MMAs of the current window are never held back by it.
+//     warps 18-19       idle (they round the CTA up to 6 warps per scheduler)
+//     warps 20-23       staging (the highest ids: the scheduler prefers them): the NEXT windows' Q / K / [V | 1] head slices
+//                       go global -> shared memory as 8-byte cp.async pieces straight into the UMMA canonical layouts (up
+//                       to three operand sets in flight), |q|^2 per row and max |k|^2 (stabiliser), region ids and the
+//                       PRMT selector table of the window (one cp.async.bulk of a host-built table, pwa_attn_sel_table);
+//                       they also fetch the next window index from the per-head work counter.
 // The arithmetic is that of attn_tc.cu (round 1): no row-max pass (norm-bound stabiliser with an exact-max sweep as the
 // rare fallback), no online rescaling, relative-position bias folded into the QK^T MMA through one-hot / table columns,
 // multiplicative pre-softmax shift mask (window_attention.py:49-58), ones column of V for the softmax denominator,
@@ -35,8 +41,8 @@ constexpr int kStage0 = 20;       // staging warps 20-23: the HIGHEST ids -- the
 constexpr int kIssue0 = 16;       // issuer warps 16 (group 0) and 17 (group 1); warps 18, 19 idle
 constexpr int kSoft0 = 0;         // softmax warps 0-15: group = warp / 8, set = (warp / 4) % 2, TMEM lane quadrant
                                   // = warp % 4.  The two SETS of a group take alternate units of the group's unit stream, so
-                                  // that four softmax warps per scheduler feed the MUFU pipe (one warp issues an ex2 only
-                                  // every ~8 clk; measured 16 / 21 / 25 results per clk and SM with 1 / 2 / 4 warps each)
+                                  // that four softmax warps per scheduler feed the MUFU pipe (one warp alone issues an ex2
+                                  // only every ~8 clk and leaves the pipe idle between its unpack / pack instructions)
 constexpr int kStageThreads = 128;
 constexpr int kUK = 64;           // keys per unit
 constexpr int kNSB = 3;           // S / P buffers per group

@@ -32,6 +32,42 @@ __global__ void __launch_bounds__(32 * kRowGroups) colsum_f32_kernel(const float
   }
 }
 
+// Column sums of a token matrix: dst[c] = sum_r x[r][c], x [rows][C] bf16 or fp32, dst fp32.  This is the bias gradient of
+// the q|k|v projection (reference window_attention.py:28-30: three nn.Linear with bias; torch autograd sums dy over the
+// tokens there): dy = the packed dq|dk|dv rows the attention backward kernel wrote, 127 MB at the first stage.  torch's
+// generic reduction needed 36-62 us per call for it (0.5-2.3 TB/s).  blockDim is a multiple of the 16-byte vectors per
+// row, so a thread meets the same columns in every iteration: four independent vector loads in flight per thread,
+// register accumulators, one shared-memory atomic per (thread, column) and one global atomic per (CTA, column) at the end.
+template <typename T>
+__global__ void __launch_bounds__(512) colsum_rows_kernel(const T* __restrict__ x, float* __restrict__ dst, long nvec, int C) {
+  constexpr int E = 16 / (int)sizeof(T);
+  extern __shared__ float cs_s[];
+  for (int i = threadIdx.x; i < C; i += blockDim.x) cs_s[i] = 0.f;
+  __syncthreads();
+  float acc[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) acc[e] = 0.f;
+  const uint4* __restrict__ xv = reinterpret_cast<const uint4*>(x);
+  const long stride = (long)gridDim.x * blockDim.x;
+  long v = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  auto add = [&](const uint4& q) {
+    T t[E];
+    *reinterpret_cast<uint4*>(t) = q;
+#pragma unroll
+    for (int e = 0; e < E; ++e) acc[e] += to_f32(t[e]);
+  };
+  for (; v + 3 * stride < nvec; v += 4 * stride) {
+    const uint4 q0 = __ldg(xv + v), q1 = __ldg(xv + v + stride), q2 = __ldg(xv + v + 2 * stride), q3 = __ldg(xv + v + 3 * stride);
+    add(q0); add(q1); add(q2); add(q3);
+  }
+  for (; v < nvec; v += stride) add(__ldg(xv + v));
+  const int c0 = (int)(threadIdx.x % (unsigned)(C / E)) * E;
+#pragma unroll
+  for (int e = 0; e < E; ++e) atomicAdd(&cs_s[c0 + e], acc[e]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dst[i], cs_s[i]);
+}
+
 }  // namespace
 
 }  // namespace pwa
@@ -43,6 +79,28 @@ extern "C" int pwa_colsum_f32(const float* src, float* dst, int S, int64_t n, vo
   PWA_CHECK_ARG(S >= 1 && n >= 1, "pwa_colsum_f32: S=%d n=%lld", S, (long long)n);
   const long blocks = (n + 31) / 32;
   colsum_f32_kernel<<<(unsigned)blocks, 32 * kRowGroups, 0, (cudaStream_t)stream>>>(src, dst, S, (long)n);
+  PWA_CUDA_OK(cudaGetLastError());
+  return PWA_OK;
+}
+
+extern "C" int pwa_colsum_rows(const void* x, float* dst, int64_t rows, int C, int dtype, void* stream) {
+  PWA_CHECK_ARG(x != nullptr && dst != nullptr, "pwa_colsum_rows: null pointer");
+  PWA_CHECK_ARG(dtype == PWA_F32 || dtype == PWA_BF16, "pwa_colsum_rows: bad dtype %d", dtype);
+  const int E = dtype == PWA_BF16 ? 8 : 4;
+  PWA_CHECK_ARG(rows >= 0 && C >= E && C % E == 0 && C / E <= 512, "pwa_colsum_rows: rows=%lld C=%d (need C %% %d == 0, C <= %d)",
+                (long long)rows, C, E, 512 * E);
+  PWA_CHECK_ARG(((uintptr_t)x & 15) == 0, "pwa_colsum_rows: x must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  PWA_CUDA_OK(cudaMemsetAsync(dst, 0, (size_t)C * 4, st));
+  if (rows == 0) return PWA_OK;
+  const int vpr = C / E;
+  const int threads = 512 / vpr * vpr;                  // a multiple of the vectors per row: fixed columns per thread
+  const long nvec = (long)rows * vpr;
+  long blocks = (nvec + (long)threads * 4 - 1) / ((long)threads * 4);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  if (dtype == PWA_BF16) colsum_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, (size_t)C * 4, st>>>((const __nv_bfloat16*)x, dst, nvec, C);
+  else colsum_rows_kernel<float><<<(unsigned)blocks, threads, (size_t)C * 4, st>>>((const float*)x, dst, nvec, C);
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }

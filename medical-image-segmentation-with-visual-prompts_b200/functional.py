@@ -712,6 +712,24 @@ def colsum_f32(part):
     return out
 
 
+def colsum_rows(x2):
+    """[T, C] bf16 / fp32 -> fp32 [C] column sums on the pwa kernel (csrc/reduce.cu: pwa_colsum_rows): the bias gradient of a
+    Linear whose output gradient is x2 (window_attention.py:28-30).  torch's generic reduction for shapes outside the
+    kernel's envelope (C not a multiple of 16 bytes, strided rows)."""
+    _require_cuda(x2)
+    T, Cc = x2.shape
+    e = 16 // x2.element_size()
+    if x2.dtype not in (torch.float32, torch.bfloat16) or not x2.is_contiguous() or Cc % e or Cc // e > 512 or x2.data_ptr() % 16:
+        return x2.sum(dim=0, dtype=torch.float32)
+    if T == 0:
+        return torch.zeros(Cc, dtype=torch.float32, device=x2.device)
+    out = torch.empty(Cc, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device), _timed("colsum_rows", 1, float(x2.numel() * x2.element_size()), x2):
+        rc = _lib.lib.pwa_colsum_rows(_ptr(x2), _ptr(out), T, Cc, _dtype_code(x2), _stream(x2))
+    _lib.check(rc, "pwa_colsum_rows")
+    return out
+
+
 def _wgrad(dy2, x2):
     """dW = dy^T x in fp32, dy [T,Cout], x [T,Cin].  For the block's Linears the output is tiny (48x48 .. 288x96) and
     T is 10^4..10^6 tokens: cuBLAS picks a split-K kernel that takes ~50 us at enc0 whatever Cout is (1.7-3.3 TB/s).
@@ -755,7 +773,7 @@ class _MultiLinear(torch.autograd.Function):
         xshape, rows, wdts, bdt = ctx.meta
         dy2 = dy.reshape(-1, dy.shape[-1])
         dx = torch.mm(dy2, w).reshape(xshape) if ctx.needs_input_grad[0] else None
-        db = dy2.sum(dim=0, dtype=torch.float32).to(bdt) if bdt is not None and ctx.needs_input_grad[1] else None
+        db = colsum_rows(dy2).to(bdt) if bdt is not None and ctx.needs_input_grad[1] else None
         dws = [None] * len(rows)
         if any(ctx.needs_input_grad[5:]):
             dw = _wgrad(dy2, x2)
@@ -891,7 +909,7 @@ class _DropAddLnLinear(torch.autograd.Function):
         want_b = bdt is not None and ctx.needs_input_grad[10] and ds2 is not None
         want_ba = badt is not None and ctx.needs_input_grad[11]
         dx, dg, db, dbr, dbx = _ln_backward_raw(dz, s, g32, mean, rstd, ds2, want_b, want_ba and p_drop == 0.0)
-        dbias = dbr.to(bdt) if dbr is not None else (dm2.sum(dim=0, dtype=torch.float32).to(bdt) if bdt is not None and ctx.needs_input_grad[10] else None)
+        dbias = dbr.to(bdt) if dbr is not None else (colsum_rows(dm2).to(bdt) if bdt is not None and ctx.needs_input_grad[10] else None)
         if p_drop > 0.0:
             da = torch.empty_like(dx)
             dba = None
@@ -904,7 +922,7 @@ class _DropAddLnLinear(torch.autograd.Function):
                     rc = _lib.lib.pwa_dropout(_ptr(dx), _ptr(da), dx.numel(), p_drop, _ptr(seed), _dtype_code(dx), _stream(dx))
             _lib.check(rc, "pwa_dropout")
             if want_ba and dba is None:
-                dba = da.sum(dim=0, dtype=torch.float32)
+                dba = colsum_rows(da)
         else:
             da, dba = dx, dbx
         return (da.view(ashape), dx.view(ashape), dg.to(gd), db.to(bd), None, None, None, None, None, dw, dbias,

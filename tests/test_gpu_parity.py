@@ -721,6 +721,23 @@ def test_colsum_f32_matches_torch(S, shape):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("T,C", [(442368, 144), (55296, 288), (28672, 576), (1, 8), (1037, 48), (3, 4096), (0, 48), (777, 20)])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_colsum_rows_matches_float64(T, C, dtype):
+    """pwa_colsum_rows (bias gradient of the q|k|v projection, window_attention.py:28-30) against a float64 sum of the
+    same values; ragged row counts, the widest row the kernel takes, an empty matrix, and a width outside the envelope
+    (C = 20 in bf16: torch's reduction)."""
+    from pwa_b200 import functional as PF
+    torch.manual_seed(T + C)
+    x = (torch.randn(T, C, device=DEV) + 0.25).to(dtype)
+    out = PF.colsum_rows(x)
+    ref = x.double().sum(0)
+    assert out.shape == (C,) and out.dtype == torch.float32
+    scale = max(1.0, float(x.double().abs().sum(0).max())) if T else 1.0
+    assert (out.double() - ref).abs().max().item() <= 2e-6 * scale
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("T,co,ci", [(72 * 512, 48, 48), (64 * 448, 144, 48), (16384 + 8, 96, 96), (1000, 48, 48)])
 def test_token_split_weight_gradient(T, co, ci):
     """The batched token-split dW = dy^T x (bf16 operands, fp32 partials) against an fp64 GEMM; shapes that do not split
@@ -809,7 +826,10 @@ def test_reference_training_config_inside_a_cuda_graph():
         outs.append((step(x.clone().requires_grad_(True)), [p.grad.clone() for p in params]))
     assert torch.equal(outs[0][0], outs[1][0])
     for a, b in zip(outs[0][1], outs[1][1]):
-        assert rel_linf(a, b) < 1e-4          # (fp32 atomics of the prompt / bias-table gradients land in a different order)
+        # fp32 atomics (prompt dK/dV, bias tables, LayerNorm dgamma) land in a different order from run to run; where such a
+        # sum is then rounded to bf16 one ulp (2^-8) can flip and travel on through the prompt projections' backward, so the
+        # bound is bf16 rounding noise, not fp32 (a 1e-4 bound failed about once in ten full-suite runs)
+        assert rel_linf(a, b) < 2e-3
 
 
 @pytest.mark.parametrize("C,Cout", [(48, 144), (48, 48), (96, 288), (192, 576), (192, 192), (16, 48)])

@@ -34,6 +34,8 @@ STAGES = {
     "enc0_nop":  (2, (48, 48, 48), 48, 4, 0),         # no prompt tokens
     "enc0_i32":  (2, (48, 48, 48), 48, 4, 32),
     "enc1":      (4, (24, 24, 24), 96, 8, 64),        # P = 54: 1728
+    "enc1_i128": (2, (24, 24, 24), 96, 8, 128),       # the widest prompt block the tcgen05 kernels take
+    "enc1_i96":  (2, (24, 24, 24), 96, 8, 96),
     "enc2":      (4, (12, 12, 24), 192, 16, 64),      # padded to 16x16x28, P = 28: 1792
     "dec0":      (8, (12, 12, 24), 192, 4, 64),       # dh 48: 896
     "dec1":      (4, (24, 24, 24), 96, 4, 64),        # dh 24: 864

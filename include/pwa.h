@@ -243,6 +243,30 @@ int pwa_token_gemm_fwd(const void* x, const void* res, const float* gamma, const
 /* 1 iff the bf16 tcgen05 kernel supports this shape (else impl=0 falls back to the fp32-math kernel). */
 int pwa_attn_tc_supported(const pwa_attn_shape* s, int dtype);
 
+/* Window attention with DENSE position-bias / mask tensors: the literal argument form of the reference's
+ * WindowAttention.forward(q, k, v, pos_bias, mask), multi_head_attention/window_attention.py:35-58 (after the three input
+ * projections, before the output projection):
+ *     logits[i][j] = (scale * q_i . k_j + bias[b,p,h,i,j]) * mask[b,p,h,i,j];   out = dropout(softmax_j(logits)) @ v
+ * q rows [B*P*nq], k / v rows [B*P*nk] with row strides ld_* (elements) and head h at columns h*dh .. h*dh+dh-1; out /
+ * dout rows are heads*dh wide and contiguous; lse / delta fp32 [B*P*heads*nq].  bias / mask: fp32 DEVICE tensors or NULL,
+ * element (b,p,h,i,j) at b*stride[0] + p*stride[1] + h*stride[2] + i*stride[3] + j (j contiguous; stride 0 = broadcast).
+ * dbias (or NULL): fp32 buffer with bias's strides, ZEROED by the caller; the gradient is accumulated with atomics.
+ * p_drop in steps of 1/256 with the generator of pwa_attn_fwd (nq rows per window-head); seed_dev = two uint32 words on
+ * the device.  fp32 arithmetic, fp32 / bf16 I/O; head dims 3, 6, 8, 12, 16, 24, 32, 48. */
+typedef struct pwa_dense_attn {
+  int32_t B, P, heads, dh, nq, nk;
+  int32_t ld_q, ld_k, ld_v;
+  int64_t bias_stride[4];
+  int64_t mask_stride[4];
+  float scale, p_drop;
+  const void* seed_dev;
+} pwa_dense_attn;
+int pwa_attn_dense_fwd(const void* q, const void* k, const void* v, const float* bias, const float* mask, void* out, float* lse,
+                       const pwa_dense_attn* s, int dtype, void* stream);
+int pwa_attn_dense_bwd(const void* q, const void* k, const void* v, const float* bias, const float* mask, const void* out,
+                       const float* lse, const void* dout, void* dq, void* dk, void* dv, float* dbias, float* delta,
+                       const pwa_dense_attn* s, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,15 @@ class PwaAttnShape(C.Structure):
     ]
 
 
+class PwaDenseAttn(C.Structure):                     # struct pwa_dense_attn
+    _fields_ = [
+        ("B", C.c_int32), ("P", C.c_int32), ("heads", C.c_int32), ("dh", C.c_int32), ("nq", C.c_int32), ("nk", C.c_int32),
+        ("ld_q", C.c_int32), ("ld_k", C.c_int32), ("ld_v", C.c_int32),
+        ("bias_stride", C.c_int64 * 4), ("mask_stride", C.c_int64 * 4),
+        ("scale", C.c_float), ("p_drop", C.c_float), ("seed_dev", C.c_void_p),
+    ]
+
+
 class PwaError(RuntimeError):
     pass
 
@@ -73,6 +82,10 @@ def _load():
         lib.pwa_debug_fwd_timeline.argtypes = [vp, i32]
         lib.pwa_debug_fwd_timeline.restype = i32
     lib.pwa_attn_tc_supported.argtypes = [sp, i32]
+    dp = C.POINTER(PwaDenseAttn)
+    lib.pwa_attn_dense_fwd.argtypes = [vp] * 7 + [dp, i32, vp]
+    lib.pwa_attn_dense_bwd.argtypes = [vp] * 13 + [dp, i32, vp]
+    lib.pwa_attn_dense_fwd.restype = lib.pwa_attn_dense_bwd.restype = i32
     lib.pwa_attn_fwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, sp, i32, i32, vp]
     lib.pwa_attn_bwd.argtypes = [vp] * 5 + [f32p] * 4 + [u8p, vp, f32p, vp] + [vp] * 3 + [f32p] * 7 + [sp, i32, i32, vp]
     i64, f32 = C.c_int64, C.c_float
@@ -93,7 +106,7 @@ def _load():
 lib = _load()
 
 EXPORTED_SYMBOLS = ("pwa_version", "pwa_last_error", "pwa_geometry", "pwa_region_ids", "pwa_index_map", "pwa_attn_sel_table",
-                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_colsum_rows", "pwa_dropout", "pwa_dropout_colsum", "pwa_token_gemm_supported", "pwa_token_gemm_fwd", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported",
+                    "pwa_partition", "pwa_reverse", "pwa_reverse_add", "pwa_gather_rows", "pwa_colsum_f32", "pwa_colsum_rows", "pwa_dropout", "pwa_dropout_colsum", "pwa_token_gemm_supported", "pwa_token_gemm_fwd", "pwa_attn_fwd", "pwa_attn_bwd", "pwa_attn_tc_supported", "pwa_attn_dense_fwd", "pwa_attn_dense_bwd",
                     "pwa_ln_fwd", "pwa_ln_bwd", "pwa_ln_bwd2", "pwa_bias_tables_fwd", "pwa_bias_tables_bwd")
 
 

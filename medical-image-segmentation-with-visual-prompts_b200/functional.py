@@ -337,6 +337,92 @@ class _WindowAttention(torch.autograd.Function):
         return dq, dk, dv, dkp, dvp, dth, dtw, dtd, dtok, None, None, None, None, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------
+# dense-argument attention (csrc/attn_dense.cu): WindowAttention.forward(q, k, v, pos_bias, mask) as the reference takes it
+# ------------------------------------------------------------------------------------------------
+def _dense_operand(t, shape5, name):
+    """A bias / mask tensor broadcastable to [b,p,h,nq,nk] -> (fp32 tensor with a contiguous last axis, strides over
+    (b,p,h,i) with 0 for broadcast axes, the 5-d shape it was materialised in)."""
+    if t is None:
+        return None, (0, 0, 0, 0), None
+    if t.dim() > 5:
+        raise ValueError(f"WindowAttention: {name} has {t.dim()} dimensions, at most 5 ([b,p,h,n_q,n_k]) expected")
+    t5 = t.reshape((1,) * (5 - t.dim()) + tuple(t.shape))
+    for have, want in zip(t5.shape, shape5):
+        if have != 1 and have != want:
+            raise ValueError(f"WindowAttention: {name} of shape {tuple(t.shape)} does not broadcast to {tuple(shape5)}")
+    if t5.shape[-1] != shape5[-1]:
+        t5 = t5.expand(*t5.shape[:-1], shape5[-1])
+    t5 = t5.to(torch.float32).contiguous()
+    strides = tuple(0 if t5.shape[i] == 1 else t5.stride(i) for i in range(4))
+    return t5, strides, tuple(t5.shape)
+
+
+class _DenseWindowAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, bias, mask, heads, scale, p_drop, seed):
+        b, p, nq, Cc = q.shape
+        nk = k.shape[2]
+        dh = Cc // heads
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        shape5 = (b, p, heads, nq, nk)
+        bias5, bst, _ = _dense_operand(None if bias is None else bias.detach(), shape5, "pos_bias")
+        mask5, mst, _ = _dense_operand(None if mask is None else mask.detach(), shape5, "mask")
+        s = _lib.PwaDenseAttn()
+        s.B, s.P, s.heads, s.dh, s.nq, s.nk = b, p, heads, dh, nq, nk
+        s.ld_q = s.ld_k = s.ld_v = Cc
+        for i in range(4):
+            s.bias_stride[i], s.mask_stride[i] = bst[i], mst[i]
+        s.scale, s.p_drop = float(scale), float(p_drop)
+        s.seed_dev = None if seed is None else seed.data_ptr()
+        out = torch.empty_like(q)
+        lse = torch.empty((b, p, heads, nq), dtype=torch.float32, device=q.device)
+        with torch.cuda.device(q.device):
+            rc = _lib.lib.pwa_attn_dense_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(bias5), _ptr(mask5), _ptr(out), _ptr(lse), s,
+                                             _dtype_code(q), _stream(q))
+        _lib.check(rc, "pwa_attn_dense_fwd")
+        ctx.save_for_backward(q, k, v, bias5, mask5, out, lse, seed)
+        ctx.shape_struct = s
+        ctx.bias_meta = None if bias is None else (tuple(bias.shape), bias.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, bias5, mask5, out, lse, seed = ctx.saved_tensors
+        s = ctx.shape_struct
+        dout = dout.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        want_db = bias5 is not None and ctx.needs_input_grad[3]
+        dbias = torch.zeros_like(bias5) if want_db else None
+        delta = torch.empty_like(lse)
+        with torch.cuda.device(q.device):
+            rc = _lib.lib.pwa_attn_dense_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(bias5), _ptr(mask5), _ptr(out), _ptr(lse), _ptr(dout),
+                                             _ptr(dq), _ptr(dk), _ptr(dv), _ptr(dbias), _ptr(delta), s, _dtype_code(q), _stream(q))
+        _lib.check(rc, "pwa_attn_dense_bwd")
+        db = None
+        if want_db:
+            shape, dt = ctx.bias_meta
+            db = dbias.sum_to_size((1,) * (5 - len(shape)) + shape).reshape(shape).to(dt)
+        return dq, dk, dv, db, None, None, None, None, None
+
+
+def dense_window_attention(q, k, v, pos_bias, mask, heads: int, scale: float, p_drop: float = 0.0,
+                           seed: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax((scale q k^T + pos_bias) * mask) v per (sample, window, head), with the reference's literal argument form
+    (window_attention.py:45-58): q [b,p,n_q,C], k / v [b,p,n_k,C] already projected, `pos_bias` / `mask` dense tensors (or
+    None) that broadcast against [b,p,h,n_q,n_k].  Differentiable in q, k, v and pos_bias.  Returns [b,p,n_q,C]."""
+    _require_cuda(q, k, v, pos_bias, mask, seed)
+    if q.dim() != 4 or k.shape != v.shape or k.shape[:2] != q.shape[:2] or k.shape[-1] != q.shape[-1]:
+        raise ValueError(f"WindowAttention: q {tuple(q.shape)}, k {tuple(k.shape)}, v {tuple(v.shape)} are not [b,p,n,C] tensors of one window set")
+    if q.shape[-1] % heads != 0:
+        raise ValueError('WindowAttention: The dimension is not compatible with the number of heads!')
+    if not (q.dtype == k.dtype == v.dtype):
+        raise TypeError("WindowAttention: q, k, v must share a dtype")
+    if p_drop > 0 and seed is None:
+        seed = new_dropout_seed(q.device)
+    return _DenseWindowAttention.apply(q, k, v, pos_bias, mask, int(heads), float(scale), float(p_drop), seed if p_drop > 0 else None)
+
+
 def prompted_window_attention(q, k, v, kp, vp, th, tw, td, tok, ids, heads: int, ws: Sequence[int], scale: float,
                               impl: int = IMPL_AUTO, p_drop: float = 0.0, seed: Optional[torch.Tensor] = None) -> torch.Tensor:
     """q,k,v [B,P,N,C]; kp,vp [B,I,C] or None; th/tw/td [h,w,w] + tok [h,I] fp32 bias tables;

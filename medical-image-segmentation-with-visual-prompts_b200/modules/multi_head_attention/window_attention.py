@@ -65,19 +65,43 @@ class WindowAttention(nn.Module):
         a = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=lowp.get('proj'), bias_grad=False, lowp_bias=lowp.get('proj_b'))
         return a, p_proj, proj_seed
 
-    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias: Optional[BiasTables] = None,
+    def _forward_dense(self, q, k, v, pos_bias, mask, prompts, prompt_kv, drop_seed):
+        if prompts is not None or prompt_kv is not None:
+            raise ValueError("WindowAttention: with a dense pos_bias / mask the prompt rows are part of q, k, v "
+                             "(reference window_attention.py:35-41); `prompts` belongs to the BiasTables form")
+        if mask is not None and mask.dtype == torch.uint8 and mask.dim() == 2:
+            raise ValueError("WindowAttention: uint8 region ids need the BiasTables form of pos_bias")
+        p_drop = float(self.attn_drop.p) if self.training else 0.0
+        p_proj = float(self.proj_drop.p) if self.training else 0.0
+        if (p_drop > 0 or p_proj > 0) and drop_seed is None:
+            drop_seed = PF.new_dropout_seed(q.device, 4)
+        qq = PF.multi_linear(q, None, self.to_q.weight)
+        kk = PF.multi_linear(k, None, self.to_k.weight)
+        vv = PF.multi_linear(v, None, self.to_v.weight)
+        o = PF.dense_window_attention(qq, kk, vv, pos_bias, mask, self.num_heads, self.scale, p_drop,
+                                      None if drop_seed is None else drop_seed[:2])
+        o = PF.multi_linear(o, self.proj.bias, self.proj.weight)
+        return PF.seeded_dropout(o, p_proj, drop_seed[2:4]) if p_proj > 0 else o
+
+    def forward(self, q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, pos_bias=None,
                 mask: Optional[torch.Tensor] = None, prompts: Optional[torch.Tensor] = None, lowp: Optional[dict] = None,
                 proj_bias_grad: bool = True, drop_seed: Optional[torch.Tensor] = None,
                 prompt_kv: Optional[torch.Tensor] = None):
-        """q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
+        """Two argument forms.
+        (1) The reference's (window_attention.py:35-41): q [b,p,n_q,C], k / v [b,p,n_k,C] (prompt rows included by the
+        caller), `pos_bias` / `mask` dense tensors or None that broadcast against [b,p,h,n_q,n_k] (e.g. RelativePE.forward's
+        [1,h,N',N'] and get_attn_mask's [1,P,1,N',N']); every row of q is a query.  Runs the dense-argument kernels
+        (csrc/attn_dense.cu), differentiable in the bias as well.
+        (2) The block's compact form, below: the fused kernels.
+        q = k = v: normalised window tokens [B,P,N,C]; `prompts`: normalised prompt tokens [B,I,C]
         appended to the keys/values of every window; pos_bias: BiasTables; mask: uint8 region ids [P,N]
         (mask[p,i,j] = ids[p,i]==ids[p,j]) or None; lowp: optional {'qkv','kv','proj'} weights already cast to the
         compute dtype (SwinTransformerBlock packs them once per forward); drop_seed: optional int32 [4] device tensor:
         words 0-1 seed the attention dropout, words 2-3 the projection dropout (drawn here when absent); prompt_kv: `project_prompts(prompts, lowp)`
         computed by the caller ahead of time (self-attention path only), instead of `prompts`.  Returns [B,P,N,C]."""
-        if pos_bias is None or not isinstance(pos_bias, BiasTables):
-            raise NotImplementedError("WindowAttention on the fused kernels takes the compact BiasTables form of the "
-                                      "position bias (RelativePE.tables), not a dense [1,1,h,N',N'] tensor")
+        if not isinstance(pos_bias, BiasTables):
+            # the reference's literal argument form (window_attention.py:35-58): dense tensors or None
+            return self._forward_dense(q, k, v, pos_bias, mask, prompts, prompt_kv, drop_seed)
         # attention dropout (reference :57) happens INSIDE the fused kernel: the probabilities are never materialised.
         # The mask comes from a counter-based hash of (seed words, sample, window, head, query, key); it cannot be the
         # reference's torch Philox stream (that is indexed over a dense [B,P,h,N',N'] tensor which does not exist here).

@@ -178,9 +178,58 @@ def run_pair_case(ref, seed=11):
     return res
 
 
+# name, C, heads, b, p, n_q, n_k, bias shape, mask shape (None = argument omitted)
+DENSE_CASES = [
+    ("block_form", 12, 4, 2, 3, 40, 40, (1, 4, 40, 40), (1, 3, 1, 40, 40)),     # RelativePE.forward + get_attn_mask shapes
+    ("bias_only",  12, 2, 1, 2, 16, 16, (2, 16, 16), None),
+    ("mask_only",  24, 4, 2, 2, 16, 24, None, (2, 2, 1, 16, 24)),               # cross attention: n_k != n_q
+    ("plain",      12, 4, 1, 2, 16, 16, None, None),
+    ("full_rank",  12, 2, 2, 2, 8, 16, (2, 2, 2, 8, 16), (2, 1, 2, 8, 1)),      # per-sample bias, mask broadcast along keys
+]
+
+
+def run_dense_cases(ref, seed=23):
+    """The reference WindowAttention called with its literal arguments (window_attention.py:35-61): dense pos_bias / mask
+    tensors of several broadcast shapes, or None.  Output and the gradients of q, k, v, pos_bias and every parameter for
+    the loss sum(out * go), float64."""
+    res = {}
+    for name, C, heads, b, p, nq, nk, bshape, mshape in DENSE_CASES:
+        torch.manual_seed(seed)
+        mod = ref.WindowAttention(C, heads)
+        g = torch.Generator().manual_seed(seed + len(name))
+        q = _rand_like_ref_inputs(g, (b, p, nq, C))
+        k = _rand_like_ref_inputs(g, (b, p, nk, C))
+        v = _rand_like_ref_inputs(g, (b, p, nk, C))
+        bias = _rand_like_ref_inputs(g, bshape, 0.7) if bshape else None
+        mask = (torch.rand(mshape, generator=g) > 0.35).float() if mshape else None
+        go = _rand_like_ref_inputs(g, (b, p, nq, C))
+        for kk, vv in mod.state_dict().items():
+            res[f"{name}.sd.{kk}"] = vv.detach().clone().numpy()
+        for kk, vv in (("q", q), ("k", k), ("v", v), ("bias", bias), ("mask", mask), ("go", go)):
+            if vv is not None:
+                res[f"{name}.{kk}"] = vv.numpy()
+        m64 = mod.double()
+        leaves = [t.double().requires_grad_(True) for t in (q, k, v)]
+        b64 = bias.double().requires_grad_(True) if bias is not None else None
+        y = m64(*leaves, pos_bias=b64, mask=None if mask is None else mask.double())
+        (y * go.double()).sum().backward()
+        res[f"{name}.out"] = y.detach().float().numpy()
+        for kk, t in zip("qkv", leaves):
+            res[f"{name}.grad.{kk}"] = t.grad.float().numpy()
+        if b64 is not None:
+            res[f"{name}.grad.bias"] = b64.grad.float().numpy()
+        for n, prm in m64.named_parameters():
+            res[f"{name}.grad.{n}"] = prm.grad.float().numpy()
+    return res
+
+
 def main():
     ref = ref_loader.load()
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    if "--dense-only" in sys.argv:
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "attn_dense.npz"), **run_dense_cases(ref))
+        print("wrote attn_dense")
+        return
     if "--pair-only" in sys.argv:
         np.savez_compressed(os.path.join(GOLDEN_DIR, "pair_merge.npz"), **run_pair_case(ref))
         print("wrote pair_merge")
@@ -194,6 +243,7 @@ def main():
         print("wrote", case[0])
     np.savez_compressed(os.path.join(GOLDEN_DIR, "pe_small.npz"), **run_pe_case(ref))
     np.savez_compressed(os.path.join(GOLDEN_DIR, "pair_merge.npz"), **run_pair_case(ref))
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "attn_dense.npz"), **run_dense_cases(ref))
     print("done")
 
 

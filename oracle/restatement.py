@@ -350,6 +350,33 @@ def prompted_window_attention(q, k, v, kp, vp, bias, ids, scale, num_heads, drop
     return o.permute(0, 1, 3, 2, 4).reshape(B, P, N, C)
 
 
+def window_attention_module(sd: Dict[str, torch.Tensor], q, k, v, pos_bias, mask, num_heads: int, drop=None):
+    """The whole reference module with its literal arguments (window_attention.py:35-61): to_q / to_k / to_v (no bias),
+    head split c = head * dh + d, logits = (q k^T * scale + pos_bias) * mask with pos_bias / mask any tensors (or None)
+    that broadcast against [b,p,h,n_q,n_k], softmax over keys, optional keep factors `drop` [b,p,h,n_q,n_k], @ v, proj.
+    sd: to_q.weight, to_k.weight, to_v.weight, proj.weight, proj.bias.  q [b,p,n_q,C]; k, v [b,p,n_k,C]."""
+    b, p, nq, C = q.shape
+    dh = C // num_heads
+    scale = dh ** -0.5
+
+    def heads(t):
+        return t.reshape(*t.shape[:-1], num_heads, dh).permute(0, 1, 3, 2, 4)     # [b,p,h,n,dh]
+
+    qh = heads(q @ sd["to_q.weight"].t())
+    kh = heads(k @ sd["to_k.weight"].t())
+    vh = heads(v @ sd["to_v.weight"].t())
+    s = torch.matmul(qh, kh.transpose(-1, -2)) * scale
+    if pos_bias is not None:
+        s = s + pos_bias
+    if mask is not None:
+        s = s * mask
+    a = torch.softmax(s, dim=-1)
+    if drop is not None:
+        a = a * drop.to(a.dtype)
+    o = torch.matmul(a, vh).permute(0, 1, 3, 2, 4).reshape(b, p, nq, C)
+    return o @ sd["proj.weight"].t() + sd["proj.bias"]
+
+
 def split_block_params(sd: Dict[str, torch.Tensor]):
     pe = {k[3:]: v for k, v in sd.items() if k.startswith("pe.")}
     return pe

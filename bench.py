@@ -336,8 +336,12 @@ def run_ours(args):
     B = args.batch
     Workload = EncoderWorkload if args.workload == "encoder" else ModelWorkload
 
-    def build(use_checkpoint):
+    def build(use_checkpoint, policy=None):
         wl = Workload(dev, args, use_checkpoint)
+        if policy is not None:             # 'selective' (default) | 'full': see SwinTransformerBlock._tokens_forward_ckpt
+            for m in wl.model.modules():
+                if hasattr(m, "checkpoint_policy"):
+                    m.checkpoint_policy = policy
         in_dtype = dtype if args.workload == "encoder" else torch.float32
         x0 = torch.zeros(wl.in_shape, dtype=in_dtype, device=dev)
         graphed = None
@@ -457,8 +461,20 @@ def run_ours(args):
         ms2 = t2.item()
         variants[f"use_checkpoint_{str(not args.checkpoint).lower()}"] = {
             "value": round(B * world * args.steps / (ms2 / 1e3), 3), "ms_per_step": round(ms2 / args.steps, 3)}
+        if not args.checkpoint:
+            variants["use_checkpoint_true"]["policy"] = ("selective: token segments recomputed, attention results kept "
+                                                         "(the default of use_checkpoint=True here)")
         del gr2, wl2
         torch.cuda.empty_cache()
+        if not args.checkpoint and world == 1:
+            # whole-block recomputation, attention included: what torch.utils.checkpoint around forward_attn_mlp does in
+            # the reference (swin_block.py:257-260)
+            wl3, gr3, _ = build(True, "full")
+            ms3 = timed(wl3, gr3, args.steps, args.warmup)
+            variants["use_checkpoint_true_full_recompute"] = {
+                "value": round(B * args.steps / (ms3 / 1e3), 3), "ms_per_step": round(ms3 / args.steps, 3)}
+            del gr3, wl3
+            torch.cuda.empty_cache()
 
     kern, attn_launches = {}, []
     if rank == 0 and not args.no_kernels and args.dtype == "bf16":

@@ -150,8 +150,8 @@ typedef struct pwa_attn_shape {
                                   words can be refreshed by a device-side RNG op every step, which keeps a captured
                                   CUDA graph of the step valid (host scalars would be frozen into the graph)      */
   const void* sel_table;       /* optional DEVICE pointer to pwa_attn_sel_table() output [P][28][N/4] uint32 for `ids` (tcgen05
-                                  forward only): fetched per window with one bulk copy instead of being rebuilt by every
-                                  (window, head).  NULL = built in the kernel.                                         */
+                                  forward and backward): fetched per window with one bulk copy instead of being rebuilt
+                                  by every (window, head).  NULL = built in the kernel.                                */
   void* work;                  /* optional DEVICE scratch of >= 4*heads bytes (contents irrelevant, zeroed by the call on
                                   its stream): per-head work counters of the tcgen05 forward, which then hands windows
                                   to its CTAs dynamically instead of round-robin (CTAs sharing an SM do not progress

@@ -642,9 +642,18 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         if (DROP)
           for (int m = pt; m < kN; m += kProd)
             rs_s[m] = drop_row_hash(seed0, seed1, (uint32_t)bw, (uint32_t)p.heads, (uint32_t)head, kN, (uint32_t)m);
-        if (MASKED)
+        if (MASKED) {
           for (int i = pt; i < kN / 4; i += kProd)
             reinterpret_cast<uint32_t*>(ids_s)[i] = reinterpret_cast<const uint32_t*>(p.ids + (size_t)win * kN)[i];
+          if (p.sel != nullptr && pt == 0) {
+            // selector table of this window precomputed per geometry (pwa_attn_sel_table, the forward's table: the mask is
+            // symmetric): ONE bulk copy whose bytes are counted on the operand barrier, instead of ~280 instructions per
+            // service thread and window
+            constexpr uint32_t kSelBytes = kIds * (kN / 4) * 4;
+            mbar_expect_tx(&bar[bOpFull + ob], kSelBytes);
+            bulk_g2s(sel_s, reinterpret_cast<const uint8_t*>(p.sel) + (size_t)win * kSelBytes, kSelBytes, &bar[bOpFull + ob]);
+          }
+        }
       }
       for (int qi = 0; qi < 2; ++qi) {                             // query rows: Q', dO' (+ delta, lse)
         if (!(all || part == qi)) continue;
@@ -687,7 +696,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         store_chunks_b<DH, DHP / 8>(Vs, NKR * 16, j, vrow, FOLD ? one : zero, FOLD ? one : zero, zero, zero);
       }
       if (all || part == 3) {
-        if (MASKED) {
+        if (MASKED && p.sel == nullptr) {
           prod_sync();                                             // ids of every service thread are in place
           // PRMT selectors: word w of id slot s covers tokens 4w..4w+3 = packed pairs 2w (low half) and 2w+1 (high half);
           // a kept bf16 takes its own bytes (nibbles 1,0 / 3,2), a masked one the bytes of the second operand (5,4 / 7,6)

@@ -258,7 +258,7 @@ def _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=0.0, seed=0, offset=0, l
     s.scale, s.p_drop, s.seed, s.offset = float(scale), float(p_drop), int(seed), int(offset)
     s.seed_dev = None if seed_dev is None else seed_dev.data_ptr()
     s.work = None if work is None else work.data_ptr()      # forward only: per-head window counters
-    s.sel_table = None if sel is None else sel.data_ptr()   # forward only: precomputed shift-mask selectors
+    s.sel_table = None if sel is None else sel.data_ptr()   # precomputed shift-mask selectors (tcgen05 kernels)
     return s
 
 
@@ -325,7 +325,8 @@ class _WindowAttention(torch.autograd.Function):
         dth, dtw, dtd = torch.empty_like(th), torch.empty_like(tw), torch.empty_like(td)
         dtok = torch.empty_like(tok) if I else None
         delta = torch.empty_like(lse)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, seed_dev=seed,
+                          sel=sel_table_for(ids) if q.dtype == torch.bfloat16 and impl != IMPL_F32 else None)
         with torch.cuda.device(q.device), _timed("attn_bwd", 2, 8.0 * B * P * N * (N + I) * Cc, q):
             rc = _lib.lib.pwa_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(kp), _ptr(vp), _ptr(th), _ptr(tw), _ptr(td),
                                        _ptr(tok), _ptr(ids), _ptr(out), _ptr(lse), _ptr(dout), _ptr(dq), _ptr(dk),
@@ -675,7 +676,8 @@ class _WindowAttentionPacked(torch.autograd.Function):
         dth, dtw, dtd = torch.empty_like(th), torch.empty_like(tw), torch.empty_like(td)
         dtok = torch.empty_like(tok) if I else None
         delta = torch.empty_like(lse)
-        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed)
+        s = _shape_struct(B, P, Cc, heads, I, ws, scale, p_drop=p_drop, ld_qkv=C3, ld_p=2 * Cc, seed_dev=seed,
+                          sel=sel_table_for(ids) if qkv.dtype == torch.bfloat16 and impl != IMPL_F32 else None)
         q0, d0 = qkv.data_ptr(), dqkv.data_ptr()
         p0 = 0 if kvp is None else kvp.data_ptr()
         vpp = C.c_void_p

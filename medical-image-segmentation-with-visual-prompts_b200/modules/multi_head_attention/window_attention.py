@@ -49,21 +49,33 @@ class WindowAttention(nn.Module):
             return None
         return PF.multi_linear(prompts, None, self.to_k.weight, self.to_v.weight, lowp=(lowp or {}).get('kv'))
 
-    def forward_packed(self, qkv: torch.Tensor, pos_bias: BiasTables, mask, prompt_kv, lowp: dict, drop_seed=None):
-        """Self-attention from an already projected q|k|v [B,P,N,3C] (the block's fused LayerNorm + projection kernel):
-        attention + output projection with its bias, WITHOUT the projection dropout -- returns (a, p_proj, proj_seed) for
-        the block's fused dropout + residual + mlp_norm + MLP kernel, whose backward also yields proj.bias's gradient."""
-        p_drop = float(self.attn_drop.p) if self.training else 0.0
-        p_proj = float(self.proj_drop.p) if self.training else 0.0
-        if (p_drop > 0 or p_proj > 0) and drop_seed is None:
+    def _drop_rates(self):
+        return (float(self.attn_drop.p), float(self.proj_drop.p)) if self.training else (0.0, 0.0)
+
+    def attend_packed(self, qkv: torch.Tensor, pos_bias: BiasTables, mask, prompt_kv, drop_seed=None):
+        """The attention core alone: already projected q|k|v [B,P,N,3C] (+ prompt K|V [B,I,2C]) -> [B,P,N,C], attention
+        dropout seeded by words 0-1 of `drop_seed`.  (The block runs this between its two checkpointed token segments.)"""
+        p_drop, _ = self._drop_rates()
+        if p_drop > 0 and drop_seed is None:
             drop_seed = PF.new_dropout_seed(qkv.device, 4)
-        attn_seed = proj_seed = None
-        if drop_seed is not None:
-            attn_seed, proj_seed = drop_seed[:2], drop_seed[2:4]
-        o = PF.prompted_window_attention_packed(qkv, prompt_kv, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
-                                                self.num_heads, pos_bias.ws, self.scale, self.impl, p_drop=p_drop, seed=attn_seed)
-        a = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=lowp.get('proj'), bias_grad=False, lowp_bias=lowp.get('proj_b'))
-        return a, p_proj, proj_seed
+        return PF.prompted_window_attention_packed(qkv, prompt_kv, pos_bias.th, pos_bias.tw, pos_bias.td, pos_bias.tok, mask,
+                                                   self.num_heads, pos_bias.ws, self.scale, self.impl, p_drop=p_drop,
+                                                   seed=None if drop_seed is None else drop_seed[:2])
+
+    def project_out(self, o: torch.Tensor, lowp: dict, proj_bias_grad: bool = True, drop_seed=None, dropout: bool = True):
+        """Output projection with its bias and (dropout=True) the projection dropout seeded by words 2-3 of `drop_seed`
+        (reference :59-60).  dropout=False leaves the dropout to the caller's fused kernel."""
+        _, p_proj = self._drop_rates()
+        if not dropout or p_proj == 0:
+            return PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=lowp.get('proj'),
+                                   bias_grad=proj_bias_grad and dropout, lowp_bias=lowp.get('proj_b'))
+        if drop_seed is None:
+            drop_seed = PF.new_dropout_seed(o.device, 4)
+        # with projection dropout the gradient of proj.bias is a by-product of the dropout's backward pass
+        drop_db = proj_bias_grad and PF.dropout_colsum_supported(o.shape[-1])
+        a = PF.multi_linear(o, self.proj.bias, self.proj.weight, lowp=lowp.get('proj'),
+                            bias_grad=proj_bias_grad and not drop_db, lowp_bias=lowp.get('proj_b'))
+        return PF.seeded_dropout(a, p_proj, drop_seed[2:4], bias_of_x=self.proj.bias if drop_db else None)
 
     def _forward_dense(self, q, k, v, pos_bias, mask, prompts, prompt_kv, drop_seed):
         if prompts is not None or prompt_kv is not None:

@@ -33,6 +33,7 @@ from .down import PatchMerging
 
 import os as _os
 _NO_TOKEN_GEMM = _os.environ.get("PWA_NO_TOKEN_GEMM", "0") == "1"      # (A/B measurements: separate LayerNorm kernels + cuBLAS)
+_CKPT_POLICY = _os.environ.get("PWA_CHECKPOINT", "selective")           # 'selective' | 'full' (see _tokens_forward_ckpt)
 _FORCE_TOKEN_GEMM = _os.environ.get("PWA_FORCE_TOKEN_GEMM", "0") == "1"  # (tests: the fused kernels at every supported shape)
 
 
@@ -95,6 +96,7 @@ class ConsecutiveSwinBlocks(nn.Module):
         self.no_shift = tuple(0 for _ in window_size)
         self.down = down
         self.use_checkpoint = use_checkpoint
+        self.checkpoint_policy = _CKPT_POLICY
         self.swin_blocks = nn.ModuleList([
             SwinTransformerBlock(hidden_channels=hidden_channels, window_size=self.window_size,
                                  pos_bias_embed_dim=pos_bias_embed_dim, num_heads=num_heads, max_prompts=max_prompts,
@@ -182,6 +184,7 @@ class SwinTransformerBlock(nn.Module):
         self.window_size = window_size
         self.shift_size = shift_size
         self.use_checkpoint = use_checkpoint
+        self.checkpoint_policy = _CKPT_POLICY
         # submodule creation order = reference order (:118-143), so seeded init is bit-identical
         self.pe = RelativePE(embed_dim=pos_bias_embed_dim, num_heads=num_heads, max_abs_pos=window_size,
                              max_cap_dist=window_size, max_prompts=max_prompts, tokens_per_prompt=tokens_per_prompt,
@@ -227,70 +230,96 @@ class SwinTransformerBlock(nn.Module):
             kvp = self.attn.project_prompts(prompts, lowp)
         return _SideInputs(tables, lowp, kvp)
 
-    def _tokens_forward(self, xw, p, geom, cdt, drop_seed=None, side=None):
+    def _use_token_gemm(self, c, rows, dtype):
+        return (PF.layer_norm_supported(c) and PF.token_gemm_supported(c, 3 * c, dtype) and not _NO_TOKEN_GEMM
+                and (_FORCE_TOKEN_GEMM or PF.token_gemm_profitable(c, rows)))
+
+    # The token-domain work of a block (reference :215-227) in three pieces, so that activation checkpointing can wrap
+    # the two cheap ones and leave the attention kernel's results saved (see _tokens_forward):
+    def _seg_pre(self, xw, cdt, side):
+        """attn_norm + q|k|v projection: window tokens [B,P,N,C] -> (alias of xw for the shortcut, q|k|v [B,P,N,3C])."""
+        c = xw.shape[-1]
+        a_ = self.attn
+        if side.ready is not None:
+            torch.cuda.current_stream(xw.device).wait_event(side.ready)
+        if self._use_token_gemm(c, xw.numel() // c, xw.dtype):
+            # SURVEY 8f-1: LayerNorm-1 + q|k|v projection in ONE tcgen05 kernel (csrc/token_gemm.cu)
+            return PF.ln_linear_pass(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6, side.lowp['qkv'],
+                                     a_.to_q.weight, a_.to_k.weight, a_.to_v.weight)
+        if PF.layer_norm_supported(c):
+            # pwa LayerNorm kernels (csrc/ln.cu).  xw is needed again as the shortcut: its second use goes through the
+            # alias, so that both of its gradients are summed inside the LayerNorm-backward kernel
+            xw, tokens = PF.layer_norm_with_passthrough(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
+        else:
+            tokens = F.layer_norm(xw, (c,), self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt), 1e-6)
+        return xw, PF.multi_linear(tokens, None, a_.to_q.weight, a_.to_k.weight, a_.to_v.weight, lowp=side.lowp['qkv'])
+
+    def _seg_post(self, o, xw, cdt, side, drop_seed):
+        """Output projection, projection dropout, `+ shortcut`, mlp_norm, MLP Linear: (attention output, shortcut) ->
+        (y, m) with block output tokens = y + m."""
+        c = xw.shape[-1]
+        a_ = self.attn
+        lowp = side.lowp
+        _, p_proj = a_._drop_rates()
+        if self._use_token_gemm(c, xw.numel() // c, xw.dtype):
+            # projection dropout + residual add + LayerNorm-2 + MLP Linear in ONE kernel; its backward also yields the
+            # gradients of proj.bias and mlp.bias
+            a = a_.project_out(o, lowp, dropout=False)
+            return PF.drop_add_ln_linear(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6, lowp['mlp'], lowp['mlp_b'],
+                                         p_proj, None if drop_seed is None else drop_seed[2:4], self.mlp.weight, self.mlp.bias,
+                                         bias_of_a=a_.proj.bias)
+        if PF.layer_norm_supported(c):
+            # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway
+            # (d of the attention branch, and d of y which equals d of m: both only meet in y + m); the two Linears
+            # skip their own bias reductions.  mlp.bias: always.  proj.bias: only without projection dropout between proj
+            # and the add (with it, d(proj output) = mask * d(attention branch), a different column sum).
+            fuse_db = p_proj == 0
+            a = a_.project_out(o, lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
+            y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
+                                     bias_of_x=a_.proj.bias if fuse_db else None, bias_of_res=self.mlp.bias)
+            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=False, lowp_bias=lowp['mlp_b'])
+            return y, m
+        y = a_.project_out(o, lowp, drop_seed=drop_seed) + xw
+        z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
+        m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], lowp_bias=lowp['mlp_b'])
+        return y, m
+
+    def _tokens_forward(self, xw, p, geom, cdt, drop_seed=None, side=None, ckpt=False):
         """Window tokens [B,P,N,C] (= shortcut) -> (y, m) with block output tokens = y + m  (reference :215-227);
-        the last add is left to the consumer (window reverse / regroup / PatchMerging gather fuse it)."""
+        the last add is left to the consumer (window reverse / regroup / PatchMerging gather fuse it).
+        ckpt: the two token segments around the attention kernel run under activation checkpointing; the kernel's own
+        saved tensors (q|k|v, its output, the log-sum-exp) stay, so the backward recomputes two LayerNorms and two small
+        GEMMs per block but never the attention.  The [B,P,h,N',N'] logits -- what checkpointing is there to avoid in the
+        reference -- never exist here in either mode."""
         ws = tuple(self.window_size)
         ids = geom.region_ids(xw.device) if geom.masked else None
         c = xw.shape[-1]
         if side is None:
             side = self._side_inputs(p, cdt, c)
-        fused_ln = PF.layer_norm_supported(c)
-        if (fused_ln and PF.token_gemm_supported(c, 3 * c, xw.dtype) and not _NO_TOKEN_GEMM
-                and (_FORCE_TOKEN_GEMM or PF.token_gemm_profitable(c, xw.numel() // c))):
-            # SURVEY 8f-1: LayerNorm-1 + q|k|v projection in ONE tcgen05 kernel, and projection dropout + residual add +
-            # LayerNorm-2 + MLP Linear in ONE kernel (csrc/token_gemm.cu); the attention output projection stays a GEMM
-            a_ = self.attn
-            if side.ready is not None:
-                torch.cuda.current_stream(xw.device).wait_event(side.ready)
-            xw, qkv = PF.ln_linear_pass(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6, side.lowp['qkv'],
-                                        a_.to_q.weight, a_.to_k.weight, a_.to_v.weight)
-            th, tw, td, tok = side.tables
-            a, p_proj, proj_seed = a_.forward_packed(qkv, BiasTables(th, tw, td, tok, ws), ids, side.kvp, side.lowp, drop_seed)
-            return PF.drop_add_ln_linear(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6, side.lowp['mlp'], side.lowp['mlp_b'],
-                                         p_proj, proj_seed, self.mlp.weight, self.mlp.bias, bias_of_a=a_.proj.bias)
-        if fused_ln:
-            # pwa LayerNorm kernels (csrc/ln.cu); the `+ shortcut` of :222 is fused into mlp_norm
-            # (xw is needed again as the shortcut: its second use goes through the alias, so that both of its gradients
-            #  are summed inside the LayerNorm-backward kernel)
-            xw, tokens = PF.layer_norm_with_passthrough(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
-        else:
-            tokens = F.layer_norm(xw, (c,), self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt), 1e-6)
-        if side.ready is not None:
-            torch.cuda.current_stream(xw.device).wait_event(side.ready)
+        if self.training and drop_seed is None and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):
+            drop_seed = PF.new_dropout_seed(xw.device, 4)
+        run = ((lambda fn, *a: checkpoint.checkpoint(fn, *a, use_reentrant=False, preserve_rng_state=False)) if ckpt
+               else (lambda fn, *a: fn(*a)))
+        xw, qkv = run(self._seg_pre, xw, cdt, side)
         th, tw, td, tok = side.tables
-        lowp = side.lowp
-        if fused_ln:
-            # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway
-            # (d of the attention branch, and d of y which equals d of m: both only meet in y + m); the two Linears
-            # skip their own bias reductions.  mlp.bias: always.  proj.bias: only without projection dropout between proj
-            # and the add (with it, d(proj output) = mask * d(attention branch), a different column sum).
-            fuse_db = not (self.training and self.attn.proj_drop.p > 0)
-            a = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                          prompt_kv=side.kvp, lowp=lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
-            y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
-                                     bias_of_x=self.attn.proj.bias if fuse_db else None, bias_of_res=self.mlp.bias)
-            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=False,
-                                lowp_bias=lowp['mlp_b'])
-            return y, m
-        y = self.attn(q=tokens, k=tokens, v=tokens, pos_bias=BiasTables(th, tw, td, tok, ws), mask=ids,
-                      prompt_kv=side.kvp, lowp=lowp, drop_seed=drop_seed)
-        y = y + xw
-        z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
-        m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], lowp_bias=lowp['mlp_b'])
-        return y, m
+        o = self.attn.attend_packed(qkv, BiasTables(th, tw, td, tok, ws), ids, side.kvp, drop_seed)
+        return run(self._seg_post, o, xw, cdt, side, drop_seed)
 
     def _tokens_forward_ckpt(self, xw, p, geom, cdt, side=None):
         """_tokens_forward, under activation checkpointing when `use_checkpoint` is set (reference :257-260).  The
         seed words of the attention dropout AND of the projection dropout (both seeded kernels, csrc/attn.cuh and
-        csrc/dropout.cu) are drawn OUTSIDE the checkpointed region and passed in, so the recomputation sees the same masks
+        csrc/dropout.cu) are drawn OUTSIDE the checkpointed regions and passed in, so the recomputation sees the same masks
         without saving / restoring the CUDA generator state -- which a graph capture cannot do.  The reference's example
-        config (use_checkpoint, attn_drop = proj_drop = 0.1) therefore runs inside a captured step."""
+        config (use_checkpoint, attn_drop = proj_drop = 0.1) therefore runs inside a captured step.
+        `checkpoint_policy`: 'selective' (default) keeps the attention kernel's results and recomputes only the token
+        segments around it; 'full' recomputes the whole token pipeline of the block, attention included."""
         if not (self.use_checkpoint and torch.is_grad_enabled()):
             return self._tokens_forward(xw, p, geom, cdt, None, side)
         seed = None
         if self.training and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):
             seed = PF.new_dropout_seed(xw.device, 4)
+        if self.checkpoint_policy == 'selective':
+            return self._tokens_forward(xw, p, geom, cdt, seed, side, True)
         return checkpoint.checkpoint(self._tokens_forward, xw, p, geom, cdt, seed, side, use_reentrant=False,
                                      preserve_rng_state=False)
 

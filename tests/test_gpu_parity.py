@@ -814,22 +814,24 @@ def test_reference_training_config_inside_a_cuda_graph():
     l2 = g(x).clone()
     assert torch.isfinite(l1) and torch.isfinite(l2) and l1.item() != l2.item()          # new masks on every replay
     assert all(torch.isfinite(a).all() for a in g1)
-    # checkpointed == plain for identical masks: eager, same generator state for both
+    # checkpointed (both policies: token segments only / whole block incl. attention) == plain for identical masks:
+    # eager, same generator state for all three
     outs = []
-    for ckpt in (True, False):
+    for ckpt, policy in ((True, "selective"), (True, "full"), (False, "selective")):
         for blk in pair.swin_blocks:
-            blk.use_checkpoint = ckpt
+            blk.use_checkpoint, blk.checkpoint_policy = ckpt, policy
         pair.use_checkpoint = ckpt
         for p in params:
             p.grad = None
         torch.manual_seed(99)
         outs.append((step(x.clone().requires_grad_(True)), [p.grad.clone() for p in params]))
-    assert torch.equal(outs[0][0], outs[1][0])
-    for a, b in zip(outs[0][1], outs[1][1]):
-        # fp32 atomics (prompt dK/dV, bias tables, LayerNorm dgamma) land in a different order from run to run; where such a
-        # sum is then rounded to bf16 one ulp (2^-8) can flip and travel on through the prompt projections' backward, so the
-        # bound is bf16 rounding noise, not fp32 (a 1e-4 bound failed about once in ten full-suite runs)
-        assert rel_linf(a, b) < 2e-3
+    for other in outs[:2]:
+        assert torch.equal(other[0], outs[2][0])
+        for a, b in zip(other[1], outs[2][1]):
+            # fp32 atomics (prompt dK/dV, bias tables, LayerNorm dgamma) land in a different order from run to run; where
+            # such a sum is then rounded to bf16 one ulp (2^-8) can flip and travel on through the prompt projections'
+            # backward, so the bound is bf16 rounding noise, not fp32 (a 1e-4 bound failed about once in ten full-suite runs)
+            assert rel_linf(a, b) < 2e-3
 
 
 @pytest.mark.parametrize("C,Cout", [(48, 144), (48, 48), (96, 288), (192, 576), (192, 192), (16, 48)])

@@ -397,34 +397,37 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             for (int q4 = 0; q4 < 4; ++q4) {
               const float4 l4 = *reinterpret_cast<const float4*>(lse2_s + r0 + h * 16 + q4 * 4);
               const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
-              float dv[4] = {0.f, 0.f, 0.f, 0.f};
+              float nd[4] = {0.f, 0.f, 0.f, 0.f};                 // -delta of the four rows (delta_s holds the negatives)
               if (!FOLD) {
                 const float4 d4 = *reinterpret_cast<const float4*>(delta_s + r0 + h * 16 + q4 * 4);
-                dv[0] = d4.x; dv[1] = d4.y; dv[2] = d4.z; dv[3] = d4.w;
+                nd[0] = d4.x; nd[1] = d4.y; nd[2] = d4.z; nd[3] = d4.w;
               }
               float pv[4], gv[4];
-              uint32_t km[2][3] = {{0u, 0u, 0u}, {0u, 0u, 0u}};   // per row pair: masks of its first / second row, packed pair mask
+              uint32_t kmp[2] = {0u, 0u};                         // packed AND masks of the two row pairs (for P^T)
               if (DROP) {
-                drop_elem_masks(T, h * 8 + q4 * 2, km[0][0], km[0][1], km[0][2]);
-                drop_elem_masks(T, h * 8 + q4 * 2 + 1, km[1][0], km[1][1], km[1][2]);
+                kmp[0] = drop_prmt(T << ((h * 8 + q4 * 2) & 7), (h * 8 + q4 * 2) < 8 ? 0xBBAAu : 0x9988u);
+                kmp[1] = drop_prmt(T << ((h * 8 + q4 * 2 + 1) & 7), (h * 8 + q4 * 2 + 1) < 8 ? 0xBBAAu : 0x9988u);
               }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int r = q4 * 4 + e;
                 pv[e] = fast_exp2(fmaf(__uint_as_float(s[r]), c2, -lv[e]));
-                if (DROP) {                                        // d P = mask * d P~ / keep_rate, then - delta
-                  const float dpe = __uint_as_float(dp[r] & km[e >> 1][e & 1]);
-                  gv[e] = pv[e] * fmaf(dpe, keep_scale, -dv[e]);
+                if (DROP) {
+                  // d P = keep * d P~ / keep_rate, then - delta: one bit test that predicates the multiply-add (the row's
+                  // -delta is used by this thread exactly once, so it is updated in place)
+                  float t = nd[e];
+                  if (T & (1u << drop_bitpos(h * 16 + r))) t = fmaf(__uint_as_float(dp[r]), keep_scale, t);
+                  gv[e] = pv[e] * t;
                 } else {
                   const float dpe = __uint_as_float(dp[r]);
-                  gv[e] = pv[e] * (FOLD ? dpe : dpe - dv[e]);
+                  gv[e] = pv[e] * (FOLD ? dpe : dpe + nd[e]);
                 }
               }
               pk[q4 * 2] = pack_bf16(pv[0], pv[1]);
               pk[q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
               if (DROP) {                                          // (applied below, after the shift mask)
-                dmask[q4 * 2] = km[0][2];
-                dmask[q4 * 2 + 1] = km[1][2];
+                dmask[q4 * 2] = kmp[0];
+                dmask[q4 * 2 + 1] = kmp[1];
               }
               gk[q4 * 2] = pack_bf16(gv[0], gv[1]);
               gk[q4 * 2 + 1] = pack_bf16(gv[2], gv[3]);
@@ -674,7 +677,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
         const __nv_bfloat16 dhi = __float2bfloat16(-dl);
         const __nv_bfloat16 dlo = __float2bfloat16(-dl - __bfloat162float(dhi));
         store_chunks_b<DH, DHP / 8>(dOs, kN * 16, n, drow, FOLD ? dhi : zero, FOLD ? dlo : zero, zero, zero);
-        delta_s[n] = dl;
+        delta_s[n] = -dl;                                          // (the compute warps add it)
         lse2_s[n] = l2;
         wp_s[n] = __float2bfloat16(fast_exp2(-l2));
       }

@@ -37,13 +37,11 @@ __global__ void __launch_bounds__(32 * kRowGroups) colsum_f32_kernel(const float
 // tokens there): dy = the packed dq|dk|dv rows the attention backward kernel wrote, 127 MB at the first stage.  torch's
 // generic reduction needed 36-62 us per call for it (0.5-2.3 TB/s).  blockDim is a multiple of the 16-byte vectors per
 // row, so a thread meets the same columns in every iteration: four independent vector loads in flight per thread,
-// register accumulators, one shared-memory atomic per (thread, column) and one global atomic per (CTA, column) at the end.
+// register accumulators, a shared-memory transposition and one global atomic per (CTA, column) at the end.
 template <typename T>
 __global__ void __launch_bounds__(512) colsum_rows_kernel(const T* __restrict__ x, float* __restrict__ dst, long nvec, int C) {
   constexpr int E = 16 / (int)sizeof(T);
-  extern __shared__ float cs_s[];
-  for (int i = threadIdx.x; i < C; i += blockDim.x) cs_s[i] = 0.f;
-  __syncthreads();
+  extern __shared__ float part_s[];                       // [blockDim][E] partial sums
   float acc[E];
 #pragma unroll
   for (int e = 0; e < E; ++e) acc[e] = 0.f;
@@ -61,11 +59,18 @@ __global__ void __launch_bounds__(512) colsum_rows_kernel(const T* __restrict__ 
     add(q0); add(q1); add(q2); add(q3);
   }
   for (; v < nvec; v += stride) add(__ldg(xv + v));
-  const int c0 = (int)(threadIdx.x % (unsigned)(C / E)) * E;
+  // thread t holds columns (t % vpr) * E .. + E - 1: column c is summed over the blockDim / vpr threads that share it
+  // (plain shared-memory reads: fp32 shared atomics are compare-and-swap loops and took longer than the main loop)
 #pragma unroll
-  for (int e = 0; e < E; ++e) atomicAdd(&cs_s[c0 + e], acc[e]);
+  for (int e = 0; e < E; ++e) part_s[threadIdx.x * E + e] = acc[e];
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(&dst[i], cs_s[i]);
+  const int vpr = C / E, reps = blockDim.x / vpr;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int cg = c / E, e = c - cg * E;
+    float t = 0.f;
+    for (int r = 0; r < reps; ++r) t += part_s[(r * vpr + cg) * E + e];
+    atomicAdd(&dst[c], t);
+  }
 }
 
 }  // namespace
@@ -97,10 +102,11 @@ extern "C" int pwa_colsum_rows(const void* x, float* dst, int64_t rows, int C, i
   const int threads = 512 / vpr * vpr;                  // a multiple of the vectors per row: fixed columns per thread
   const long nvec = (long)rows * vpr;
   long blocks = (nvec + (long)threads * 4 - 1) / ((long)threads * 4);
-  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
   if (blocks < 1) blocks = 1;
-  if (dtype == PWA_BF16) colsum_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, (size_t)C * 4, st>>>((const __nv_bfloat16*)x, dst, nvec, C);
-  else colsum_rows_kernel<float><<<(unsigned)blocks, threads, (size_t)C * 4, st>>>((const float*)x, dst, nvec, C);
+  const size_t smem = (size_t)threads * 16;
+  if (dtype == PWA_BF16) colsum_rows_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, smem * 2, st>>>((const __nv_bfloat16*)x, dst, nvec, C);
+  else colsum_rows_kernel<float><<<(unsigned)blocks, threads, smem, st>>>((const float*)x, dst, nvec, C);
   PWA_CUDA_OK(cudaGetLastError());
   return PWA_OK;
 }

@@ -637,7 +637,8 @@ def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default 20; 5 for --impl reference, whose steps take seconds)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="encoder", choices=["encoder", "model"])
@@ -657,6 +658,8 @@ def main():
     ap.add_argument("--cuda-profiler-range", action="store_true",
                     help="bracket the HBM-resident timed region with cudaProfilerStart/Stop (for ncu --profile-from-start off)")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 5 if args.impl == "reference" else 20
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)

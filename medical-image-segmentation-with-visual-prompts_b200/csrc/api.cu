@@ -21,6 +21,7 @@ static int fill(AttnParams& p, const pwa_attn_shape* s, const char* who) {
     if (t > 255) t = 255;
     if (s->p_drop > 0.f && t == 0) t = 1;
     p.drop_thresh = (uint32_t)t;
+    p.drop_planes = drop_thresh_planes(p.drop_thresh);
     p.inv_keep = 256.f / (float)(256 - t);
     p.drop_seed = (const uint32_t*)s->seed_dev;
     p.work = (unsigned int*)s->work;

@@ -4,6 +4,11 @@
 
 namespace pwa {
 
+// dropout threshold as bit planes: tb[k] = all ones iff bit k of the threshold is set (see drop_keep_word below)
+struct DropThresh {
+  uint32_t tb[8];
+};
+
 struct AttnParams {
   const void *q, *k, *v, *kp, *vp;
   const float *th, *tw, *td, *tok;
@@ -20,6 +25,9 @@ struct AttnParams {
   // attention dropout (window_attention.py:57): 0 = off.  An element (query n, key j) is dropped iff its byte of a
   // counter-based hash is < drop_thresh (probability drop_thresh / 256); kept probabilities are scaled by inv_keep.
   uint32_t drop_thresh;
+  DropThresh drop_planes;      // drop_thresh_planes(drop_thresh), filled by the dispatcher: read by the tcgen05 kernels straight
+                               // from the constant bank (computed in the kernel, ptxas rebuilt the eight masks for every keep
+                               // word under register pressure: 0.75 instructions per logit of the backward)
   float inv_keep;
   const uint32_t* drop_seed;   // DEVICE pointer to two 32-bit seed words (graph-replay safe), or null
   uint32_t seed_host[2];       // used when drop_seed is null
@@ -49,10 +57,6 @@ __device__ __forceinline__ uint32_t drop_row_hash(uint32_t s0, uint32_t s1, uint
                                                  uint32_t n) {
   return drop_mix(s0 + ((bw * heads + head) * N + n) * 0x85EBCA77u) ^ s1;
 }
-// tb[k] = all ones iff bit k of the threshold is set
-struct DropThresh {
-  uint32_t tb[8];
-};
 __host__ __device__ inline DropThresh drop_thresh_planes(uint32_t thresh) {
   DropThresh t;
   for (int k = 0; k < 8; ++k) t.tb[k] = ((thresh >> k) & 1u) ? 0xffffffffu : 0u;

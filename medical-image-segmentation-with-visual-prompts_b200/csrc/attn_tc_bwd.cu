@@ -214,6 +214,9 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   const int NKR = kN + 128;                        // rows allocated for key-side operands (prompt block issued as M = 128)
   const BwdSmem L = bwd_layout(KS, DHP, NKT, p.wh, p.ww, p.wd, p.I, MASKED);
   const int OPB = L.opb, GSB = L.gsb;
+  // (GSB, OPB are 1 or 2, but `& (GSB - 1)` / a division-free form instead of `% GSB`, `/ GSB` in the unit loop were both
+  //  measured SLOWER in the masked dropout variants, 708 -> 744-765 us at enc0: ptxas then spills 40 bytes more inside the
+  //  unit loop at the 72-register cap; the divisions stay)
   uint8_t* Qa = smem + L.qaug;
   uint8_t* Ka = smem + L.kaug;
   float* gth_s = reinterpret_cast<float*>(smem + L.gth);
@@ -226,7 +229,7 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
   const float c2 = p.scale * 1.4426950408889634f;
   const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
   const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
-  const DropThresh dth = drop_thresh_planes(DROP ? p.drop_thresh : 0u);
+  const DropThresh& dth = p.drop_planes;          // constant bank (filled by the dispatcher)
   const float keep_scale = DROP ? p.inv_keep : 1.f;
   const __nv_bfloat16 one = __float2bfloat16(1.f), zero = __float2bfloat16(0.f);
 
@@ -392,7 +395,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             tmem_ld16(trow + cP + wg * 32 + h * 16, dp);
             tmem_wait_ld();
             uint32_t pk[8], gk[8];
-            uint32_t dmask[DROP ? 8 : 1];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               const float4 l4 = *reinterpret_cast<const float4*>(lse2_s + r0 + h * 16 + q4 * 4);
@@ -403,11 +405,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
                 nd[0] = d4.x; nd[1] = d4.y; nd[2] = d4.z; nd[3] = d4.w;
               }
               float pv[4], gv[4];
-              uint32_t kmp[2] = {0u, 0u};                         // packed AND masks of the two row pairs (for P^T)
-              if (DROP) {
-                kmp[0] = drop_prmt(T << ((h * 8 + q4 * 2) & 7), (h * 8 + q4 * 2) < 8 ? 0xBBAAu : 0x9988u);
-                kmp[1] = drop_prmt(T << ((h * 8 + q4 * 2 + 1) & 7), (h * 8 + q4 * 2 + 1) < 8 ? 0xBBAAu : 0x9988u);
-              }
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
                 const int r = q4 * 4 + e;
@@ -425,10 +422,6 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
               }
               pk[q4 * 2] = pack_bf16(pv[0], pv[1]);
               pk[q4 * 2 + 1] = pack_bf16(pv[2], pv[3]);
-              if (DROP) {                                          // (applied below, after the shift mask)
-                dmask[q4 * 2] = kmp[0];
-                dmask[q4 * 2 + 1] = kmp[1];
-              }
               gk[q4 * 2] = pack_bf16(gv[0], gv[1]);
               gk[q4 * 2 + 1] = pack_bf16(gv[2], gv[3]);
             }
@@ -448,7 +441,8 @@ __global__ void __launch_bounds__(kThreadsB, 1) attn_bwd_tc_kernel(AttnParams p)
             }
             if (DROP) {
 #pragma unroll
-              for (int w = 0; w < 8; ++w) pk[w] &= dmask[w];       // dropped P^T entries do not reach dV
+              for (int w = 0; w < 8; ++w)                          // dropped P^T entries do not reach dV (pair h * 8 + w of the tile)
+                pk[w] &= drop_prmt(T << ((h * 8 + w) & 7), (h * 8 + w) < 8 ? 0xBBAAu : 0x9988u);
             }
             tmem_st8(trow + cS + wg * 32 + h * 8, pk);             // packed over this warpgroup's own consumed columns
             tmem_st8(trow + cP + wg * 32 + h * 8, gk);

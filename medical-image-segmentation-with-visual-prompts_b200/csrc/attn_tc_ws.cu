@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreadsW, 1) attn_fwd_ws_kernel(AttnParams p)
     const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * GC);
     const uint32_t seed0 = DROP ? (p.drop_seed ? p.drop_seed[0] : p.seed_host[0]) : 0u;
     const uint32_t seed1 = DROP ? (p.drop_seed ? p.drop_seed[1] : p.seed_host[1]) : 0u;
-    const DropThresh dth = drop_thresh_planes(DROP ? p.drop_thresh : 0u);
+    const DropThresh& dth = p.drop_planes;          // constant bank (filled by the dispatcher)
     uint32_t ucount = 0, tcount = 0;                                // units / tiles of this GROUP so far (both sets count all)
     WS_PROF_DECL(8);          // 0 wait operands, 1 window setup, 3 unit loop, 5 wait O, 6 epilogue
     for (int it = 0;; ++it) {

@@ -39,7 +39,7 @@ struct AttnParams {
 // ---- dropout mask (v2): bit-sliced Bernoulli, 32 keys of one query row per call ----------------------------------
 // The keep decisions of query row n for the 32 keys of key chunk c = j >> 5 (j = key index over content AND prompt
 // keys) come out of ONE call: a per-row hash (full avalanche mix, once per row and window-head) is folded with the
-// chunk index, eight 32-bit planes are derived from it with one multiply + xor-fold each, and the 8-bit numbers formed
+// chunk index, eight 32-bit planes are derived from it (the upper halves of two products each), and the 8-bit numbers formed
 // by the planes (plane k = bit k) are compared with the threshold bit-sliced: one 3-input logic op per plane for all 32
 // keys at once.  Key j is kept iff its number is >= thresh (drop probability thresh / 256).  About 1.1 instructions
 // per element instead of the ~5 (plus byte compares and selects) of one hash per 2x2 block.
@@ -65,16 +65,24 @@ __host__ __device__ inline DropThresh drop_thresh_planes(uint32_t thresh) {
 __host__ __device__ constexpr int drop_bitpos(int jj) {
   return ((jj >> 1) < 8 ? ((jj & 1) ? 31 : 23) : ((jj & 1) ? 15 : 7)) - ((jj >> 1) & 7);
 }
+__device__ __forceinline__ uint32_t drop_join_hi(uint32_t a, uint32_t b) {     // (a >> 16) | (b & 0xffff0000)
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
 // keep bits of (row hash, key chunk): bit drop_bitpos(jj) = 1 iff key 32 * chunk + jj is kept
 __device__ __forceinline__ uint32_t drop_keep_word(uint32_t row_hash, uint32_t chunk, const DropThresh& t) {
   uint32_t y = (row_hash ^ (chunk * 0x9E3779B1u)) * 0x2C1B3C6Du;
   y ^= y >> 15;
-  constexpr uint32_t M[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+  // plane k = [high half of y * MB[k] : high half of y * MA[k]]: the well-mixed upper bits of two products, joined by ONE PRMT
+  // (a single product folded with `w ^= w >> 16` cost a shift and two more logic ops per plane on the ALU pipe, the pipe
+  // that binds the dropout variants, and left keys jj and jj + 16 of a chunk correlated at 0.06)
+  constexpr uint32_t MA[8] = {0x9E3779B1u, 0x85EBCA77u, 0xC2B2AE3Du, 0x27D4EB2Fu, 0x165667B1u, 0xD3A2646Du, 0xFD7046C5u, 0xB55A4F09u};
+  constexpr uint32_t MB[8] = {0x7FEB352Du, 0x846CA68Bu, 0x2C1B3C6Du, 0x297A2D39u, 0x9E485565u, 0xEF1D6B47u, 0x68E31DA5u, 0xB5297A4Du};
   uint32_t lt = 0u;                        // bit-sliced (number < thresh), planes from the least significant up
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    uint32_t w = y * M[k];
-    w ^= w >> 16;
+    const uint32_t w = drop_join_hi(y * MA[k], y * MB[k]);
     lt = (~w & (lt | t.tb[k])) | (lt & t.tb[k]);    // thresh bit 1: ~w | lt ; 0: ~w & lt   (majority of ~w, lt, tb)
   }
   return ~lt;

@@ -212,6 +212,7 @@ def dense_bias(th, tw, td, tok) -> torch.Tensor:
 # attention + block
 # --------------------------------------------------------------------------------------
 _DROP_PLANE_MUL = (0x9E3779B1, 0x85EBCA77, 0xC2B2AE3D, 0x27D4EB2F, 0x165667B1, 0xD3A2646D, 0xFD7046C5, 0xB55A4F09)
+_DROP_PLANE_MUL_B = (0x7FEB352D, 0x846CA68B, 0x2C1B3C6D, 0x297A2D39, 0x9E485565, 0xEF1D6B47, 0x68E31DA5, 0xB5297A4D)
 
 
 def _drop_bitpos(jj):
@@ -232,7 +233,7 @@ def dropout_keep_factor(seed_words, B, P, num_heads, N, NK, p_drop):
     over a tensor they never materialise, so parity is: same distribution (Bernoulli, rate in steps of 1/256,
     inverse-keep-rate scaling) and exact agreement with THIS mask for given seed words.
     Per (sample*window, head, query row) one avalanche hash; per 32-key chunk a folded value y; eight planes
-    fold16(y * M_k); key jj of the chunk reads bit drop_bitpos(jj) of every plane, plane k = bit k of an 8-bit number,
+    [hi16(y * MB_k) : hi16(y * MA_k)]; key jj of the chunk reads bit drop_bitpos(jj) of every plane, plane k = bit k of an 8-bit number,
     kept iff number >= round(256 p)."""
     M = np.uint64(0xFFFFFFFF)
     u = np.uint64
@@ -255,9 +256,8 @@ def dropout_keep_factor(seed_words, B, P, num_heads, N, NK, p_drop):
     y ^= y >> u(15)
     pos = np.array([_drop_bitpos(int(v) & 31) for v in range(NK)], dtype=np.uint64)[None, None, None, :]
     num = np.zeros(y.shape, dtype=np.uint64)
-    for k, mk in enumerate(_DROP_PLANE_MUL):
-        w = (y * u(mk)) & M
-        w ^= w >> u(16)
+    for k, (ma, mb) in enumerate(zip(_DROP_PLANE_MUL, _DROP_PLANE_MUL_B)):
+        w = (((y * u(ma)) & M) >> u(16)) | ((y * u(mb)) & u(0xFFFF0000))
         num |= ((w >> pos) & u(1)) << u(k)
     keep = num >= u(t)
     return torch.from_numpy(keep.astype(np.float64) * (256.0 / (256 - t))).reshape(B, P, num_heads, N, NK)
@@ -285,9 +285,8 @@ def dropout_keep_factor_torch(seed_words, bw0, n_bw, num_heads, N, NK, p_drop, d
     y = y ^ (y >> 15)
     pos = torch.tensor([_drop_bitpos(v & 31) for v in range(NK)], dtype=torch.int64, device=device).reshape(1, 1, 1, -1)
     num = torch.zeros_like(y)
-    for k, mk in enumerate(_DROP_PLANE_MUL):
-        w = (y * mk) & M
-        w = w ^ (w >> 16)
+    for k, (ma, mb) in enumerate(zip(_DROP_PLANE_MUL, _DROP_PLANE_MUL_B)):
+        w = (((y * ma) & M) >> 16) | ((y * mb) & 0xFFFF0000)
         num = num | (((w >> pos) & 1) << k)
     return (num >= t).to(torch.float64) * (256.0 / (256 - t))
 

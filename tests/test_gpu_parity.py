@@ -829,9 +829,10 @@ def test_reference_training_config_inside_a_cuda_graph():
         assert torch.equal(other[0], outs[2][0])
         for a, b in zip(other[1], outs[2][1]):
             # fp32 atomics (prompt dK/dV, bias tables, LayerNorm dgamma) land in a different order from run to run; where
-            # such a sum is then rounded to bf16 one ulp (2^-8) can flip and travel on through the prompt projections'
-            # backward, so the bound is bf16 rounding noise, not fp32 (a 1e-4 bound failed about once in ten full-suite runs)
-            assert rel_linf(a, b) < 2e-3
+            # such a sum is then rounded to bf16 one ulp can flip (2^-8 relative: observed 2.05e-3 of the tensor's maximum
+            # in 2 of 5 full-suite runs) and travel on through the prompt projections' backward.  The bound is a few bf16
+            # ulps; a wrong or re-drawn dropout mask in the recomputation changes these gradients by O(1).
+            assert rel_linf(a, b) < 1e-2
 
 
 @pytest.mark.parametrize("C,Cout", [(48, 144), (48, 48), (96, 288), (192, 576), (192, 192), (16, 48)])

@@ -887,7 +887,8 @@ def test_block_with_fused_token_gemms_matches_separate_kernels():
         p = (0.2 * torch.randn(2, 64, 48, device=DEV)).bfloat16()
         res = []
         for off in (False, True):
-            sb._NO_TOKEN_GEMM = off
+            # (the profitability policy would keep this small map on the separate kernels: force the fused ones)
+            sb._NO_TOKEN_GEMM, sb._FORCE_TOKEN_GEMM = off, not off
             try:
                 for prm in blk.parameters():
                     prm.grad = None
@@ -897,10 +898,44 @@ def test_block_with_fused_token_gemms_matches_separate_kernels():
                 y.float().square().mean().backward()
                 res.append((y.detach(), xg.grad, pg.grad, [q.grad.clone() for q in blk.parameters()]))
             finally:
-                sb._NO_TOKEN_GEMM = False
+                sb._NO_TOKEN_GEMM = sb._FORCE_TOKEN_GEMM = False
         assert rel_linf(res[0][0], res[1][0]) < 1e-2
         assert rel_linf(res[0][1], res[1][1]) < 2e-2 and rel_linf(res[0][2], res[1][2]) < 2e-2
         gmax = max(g.abs().max().item() for g in res[1][3])
         for (n, _), a, b in zip(blk.named_parameters(), res[0][3], res[1][3]):
             den = max(b.abs().max().item(), 1e-3 * gmax)
             assert (a - b).abs().max().item() / den < 2e-2, n
+
+
+def test_checkpoint_policies_on_the_fused_token_gemm_path():
+    """use_checkpoint with both policies ('selective': token segments around the attention kernel; 'full': the whole token
+    pipeline) on the FUSED token-GEMM kernels, dropout 0.1, inside a pair: same loss bit for bit and the same gradients (a
+    few bf16 ulps: atomics order) as without checkpointing, for identical seed words."""
+    import importlib
+    sb = importlib.import_module(pwa_b200.SwinTransformerBlock.__module__)
+    torch.manual_seed(17)
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=48, num_heads=4, pos_bias_embed_dim=64, max_prompts=1,
+                                          tokens_per_prompt=64, window_size=(8, 8, 4), down=True, use_checkpoint=True,
+                                          attn_drop=0.1, proj_drop=0.1).to(DEV).train()
+    prompts = [(0.2 * torch.randn(2, 64, 48, device=DEV)).bfloat16().requires_grad_(True) for _ in range(2)]
+    x = torch.randn(2, 48, 16, 16, 8, device=DEV).bfloat16()
+    params = list(pair.parameters()) + prompts
+    sb._FORCE_TOKEN_GEMM = True
+    try:
+        outs = []
+        for ckpt, policy in ((True, "selective"), (True, "full"), (False, "selective")):
+            for blk in pair.swin_blocks:
+                blk.use_checkpoint, blk.checkpoint_policy = ckpt, policy
+            pair.use_checkpoint = ckpt
+            for q in params:
+                q.grad = None
+            torch.manual_seed(123)
+            loss = pair(x.clone().requires_grad_(True), tuple(prompts)).float().square().mean()
+            loss.backward()
+            outs.append((loss.detach(), [q.grad.clone() for q in params]))
+    finally:
+        sb._FORCE_TOKEN_GEMM = False
+    for other in outs[:2]:
+        assert torch.equal(other[0], outs[2][0])
+        for a, b in zip(other[1], outs[2][1]):
+            assert rel_linf(a, b) < 1e-2

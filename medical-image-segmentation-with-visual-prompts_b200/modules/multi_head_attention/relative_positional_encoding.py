@@ -55,9 +55,13 @@ class RelativePE(nn.Module):
                                        f"{enc_tok.shape[0]}")
                 w_tok = self.weights_token
             dims = (dim_h, dim_w, dim_d)
-            if all(getattr(self, f"relative_dist_{ax}").shape[0] >= n for ax, n in zip(_AXES, dims)):
-                return PF.bias_tables(self.enc_content_h, self.enc_content_w, self.enc_content_d, self.weights_content_h,
-                                      self.weights_content_w, self.weights_content_d, enc_tok, w_tok, dims)
+            if not all(getattr(self, f"relative_dist_{ax}").shape[0] >= n for ax, n in zip(_AXES, dims)):
+                raise RuntimeError(f"RelativePE: window {dims} exceeds max_abs_pos of the module")
+            return PF.bias_tables(self.enc_content_h, self.enc_content_w, self.enc_content_d, self.weights_content_h,
+                                  self.weights_content_w, self.weights_content_d, enc_tok, w_tok, dims)
+        # Parameters in HOST memory (state-dict inspection, float64 checks of the table algebra against the reference in
+        # tests/test_host_cpu.py): the same few-KB parameter -> table algebra in torch.  Not a compute path: the kernels
+        # only ever see tables built on the device above, and the blocks raise on CPU tensors.
         out = []
         for ax, n in zip(_AXES, (dim_h, dim_w, dim_d)):
             enc = getattr(self, f"enc_content_{ax}")

@@ -56,14 +56,13 @@ class PatchMerging(nn.Module):
         else:
             parts = [x[:, :, a::2, b::2, :] for a, b in _OFFS2]
         t = torch.cat(parts, dim=1).permute(0, 2, 3, 4, 1)             # [B,h/2,w/2,d',kC] channels last
-        dt = t.dtype
         from ... import functional as PF
-        if t.is_cuda and PF.layer_norm_supported(t.shape[-1]):
-            t = PF.layer_norm(t.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps)
-            t = PF.multi_linear(t, None, self.reduction.weight)
-        else:
-            t = F.layer_norm(t, self.norm.normalized_shape, self.norm.weight.to(dt), self.norm.bias.to(dt), self.norm.eps)
-            t = F.linear(t, self.reduction.weight.to(dt))
+        if not t.is_cuda:
+            raise RuntimeError("pwa_b200.PatchMerging runs on CUDA (sm_100a) only; there is no CPU path")
+        if not PF.layer_norm_supported(t.shape[-1]):
+            raise NotImplementedError(f"PatchMerging: {t.shape[-1]} merged channels (need a multiple of 4, at most 2048)")
+        t = PF.layer_norm(t.contiguous(), self.norm.weight, self.norm.bias, self.norm.eps)
+        t = PF.multi_linear(t, None, self.reduction.weight)
         return t.permute(0, 4, 1, 2, 3)
 
     def named_parameters_body(self):

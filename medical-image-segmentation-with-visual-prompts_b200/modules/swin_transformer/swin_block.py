@@ -223,10 +223,7 @@ class SwinTransformerBlock(nn.Module):
         if p is not None:
             if p.dim() != 3 or p.shape[-1] != c:
                 raise ValueError(f"SwinTransformerBlock: prompt tokens must be [B, I, {c}], got {tuple(p.shape)}")
-            if PF.layer_norm_supported(c):
-                prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6)
-            else:
-                prompts = F.layer_norm(p.to(cdt), (c,), self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt), 1e-6)
+            prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6)
             kvp = self.attn.project_prompts(prompts, lowp)
         return _SideInputs(tables, lowp, kvp)
 
@@ -246,12 +243,9 @@ class SwinTransformerBlock(nn.Module):
             # LayerNorm-1 + q|k|v projection in ONE tcgen05 kernel (csrc/token_gemm.cu)
             return PF.ln_linear_pass(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6, side.lowp['qkv'],
                                      a_.to_q.weight, a_.to_k.weight, a_.to_v.weight)
-        if PF.layer_norm_supported(c):
-            # pwa LayerNorm kernels (csrc/ln.cu).  xw is needed again as the shortcut: its second use goes through the
-            # alias, so that both of its gradients are summed inside the LayerNorm-backward kernel
-            xw, tokens = PF.layer_norm_with_passthrough(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
-        else:
-            tokens = F.layer_norm(xw, (c,), self.attn_norm.weight.to(cdt), self.attn_norm.bias.to(cdt), 1e-6)
+        # pwa LayerNorm kernels (csrc/ln.cu).  xw is needed again as the shortcut: its second use goes through the alias, so
+        # that both of its gradients are summed inside the LayerNorm-backward kernel
+        xw, tokens = PF.layer_norm_with_passthrough(xw, self.attn_norm.weight, self.attn_norm.bias, 1e-6)
         return xw, PF.multi_linear(tokens, None, a_.to_q.weight, a_.to_k.weight, a_.to_v.weight, lowp=side.lowp['qkv'])
 
     def _seg_post(self, o, xw, cdt, side, drop_seed):
@@ -268,20 +262,15 @@ class SwinTransformerBlock(nn.Module):
             return PF.drop_add_ln_linear(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6, lowp['mlp'], lowp['mlp_b'],
                                          p_proj, None if drop_seed is None else drop_seed[2:4], self.mlp.weight, self.mlp.bias,
                                          bias_of_a=a_.proj.bias)
-        if PF.layer_norm_supported(c):
-            # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway
-            # (d of the attention branch, and d of y which equals d of m: both only meet in y + m); the two Linears
-            # skip their own bias reductions.  mlp.bias: always.  proj.bias: only without projection dropout between proj
-            # and the add (with it, d(proj output) = mask * d(attention branch), a different column sum).
-            fuse_db = p_proj == 0
-            a = a_.project_out(o, lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
-            y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
-                                     bias_of_x=a_.proj.bias if fuse_db else None, bias_of_res=self.mlp.bias)
-            m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=False, lowp_bias=lowp['mlp_b'])
-            return y, m
-        y = a_.project_out(o, lowp, drop_seed=drop_seed) + xw
-        z = F.layer_norm(y, (c,), self.mlp_norm.weight.to(cdt), self.mlp_norm.bias.to(cdt), 1e-6)
-        m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], lowp_bias=lowp['mlp_b'])
+        # the gradients of proj.bias and mlp.bias are column sums of tensors the mlp_norm backward streams anyway (d of the
+        # attention branch, and d of y which equals d of m: both only meet in y + m); the two Linears skip their own bias
+        # reductions.  mlp.bias: always.  proj.bias: only without projection dropout between proj and the add (with it,
+        # d(proj output) = mask * d(attention branch), a different column sum).
+        fuse_db = p_proj == 0
+        a = a_.project_out(o, lowp, proj_bias_grad=not fuse_db, drop_seed=drop_seed)
+        y, z = PF.add_layer_norm(a, xw, self.mlp_norm.weight, self.mlp_norm.bias, 1e-6,
+                                 bias_of_x=a_.proj.bias if fuse_db else None, bias_of_res=self.mlp.bias)
+        m = PF.multi_linear(z, self.mlp.bias, self.mlp.weight, lowp=lowp['mlp'], bias_grad=False, lowp_bias=lowp['mlp_b'])
         return y, m
 
     def _tokens_forward(self, xw, p, geom, cdt, drop_seed=None, side=None, ckpt=False):
@@ -294,6 +283,9 @@ class SwinTransformerBlock(nn.Module):
         ws = tuple(self.window_size)
         ids = geom.region_ids(xw.device) if geom.masked else None
         c = xw.shape[-1]
+        if not PF.layer_norm_supported(c):
+            raise NotImplementedError(f"SwinTransformerBlock: hidden_channels = {c} (the LayerNorm kernels need a multiple of "
+                                      "4, at most 2048); there is no torch fallback")
         if side is None:
             side = self._side_inputs(p, cdt, c)
         if self.training and drop_seed is None and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):

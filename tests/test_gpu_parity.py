@@ -297,6 +297,40 @@ def test_pair_with_merge_all_gradients_vs_reference_golden(tag, mld, dtype, rtol
         assert rel_linf(g, t("grad." + n)) < (rtol if dtype == torch.float32 else _bf16_param_tol(n, (4, 4, 2))), n
 
 
+@pytest.mark.parametrize("mld,C,heads", [(True, 192, 4), (False, 384, 16)])
+def test_pair_with_wide_patch_merging_vs_oracle(mld, C, heads):
+    """PatchMerging norms wider than 1024 channels (8 x 192 = 4 x 384 = 1536: the reference's last encoder stages,
+    down.py:13-14) inside the pair's token pipeline, forward and gradients against the float64 oracle."""
+    from oracle import model_init
+    torch.manual_seed(C)
+    E, I, ws, dims = 16, 32, (8, 8, 4), (8, 8, 8)
+    sd = model_init.pair_state_dict(C, heads, E, I, ws, down=True, merge_last_dim=mld)
+    pair = pwa_b200.ConsecutiveSwinBlocks(hidden_channels=C, num_heads=heads, pos_bias_embed_dim=E, max_prompts=1,
+                                          tokens_per_prompt=I, window_size=ws, down=True, merge_last_dim=mld)
+    sd = {k: v for k, v in sd.items() if k in pair.state_dict()}
+    pair.load_state_dict(sd, strict=False)
+    full = {k: v.detach().double().clone().requires_grad_(v.is_floating_point()) for k, v in pair.state_dict().items()}
+    pair.to(DEV)
+    x = torch.randn(1, C, *dims)
+    ps = [0.3 * torch.randn(1, I, C) for _ in range(2)]
+    go = None
+    x64 = x.double().requires_grad_(True)
+    p64 = [t.double().requires_grad_(True) for t in ps]
+    ref = R.pair_forward(full, x64, p64, ws, heads, True, mld)
+    go = torch.randn(ref.shape)
+    (ref * go.double()).sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    pd = [t.to(DEV).requires_grad_(True) for t in ps]
+    y = pair(xd, tuple(pd))
+    assert y.shape == ref.shape and rel_linf(y, ref) < RTOL_F32
+    y.backward(go.to(DEV))
+    assert rel_linf(xd.grad, x64.grad) < RTOL_F32
+    for a, b in zip(pd, p64):
+        assert rel_linf(a.grad, b.grad) < RTOL_F32
+    for n in ("merge.norm.weight", "merge.norm.bias", "merge.reduction.weight"):
+        assert rel_linf(dict(pair.named_parameters())[n].grad, full[n].grad) < RTOL_F32, n
+
+
 def test_full_size_attention_properties():
     """BASELINE-size (enc0: C=48, h=4, P=432) checks that need no oracle run: rows of softmax sum to one
     (v = 1 -> out = 1), linearity in v, and the masked/unmasked kernels agree when all ids are equal."""
@@ -329,7 +363,7 @@ def test_block_full_size_runs_and_matches_oracle_sample():
     assert rel_linf(y16, y32) < RTOL_BF16
 
 
-@pytest.mark.parametrize("C", [12, 48, 96, 192, 384, 768])
+@pytest.mark.parametrize("C", [12, 48, 96, 192, 384, 768, 1536, 2048])
 @pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-5), (torch.bfloat16, RTOL_BF16)])
 @pytest.mark.parametrize("with_res", [False, True])
 def test_layer_norm_kernels(C, dtype, rtol, with_res):

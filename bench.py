@@ -377,10 +377,12 @@ def run_ours(args):
                 flat.div_(world)
         return loss
 
-    def timed(w, gr, steps, warmup):
+    def timed(w, gr, steps, warmup, count=False):
         for i in range(warmup):
             run_step(w, gr, xdev[i % len(xdev)])
         barrier()
+        if count:                                   # gpu_launches: kernels of the K timed steps only, not of the warm-up
+            KernelStats.reset(enabled=True, timing=False)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         e0.record()
@@ -400,10 +402,10 @@ def run_ours(args):
             run_step(wl, graphed, xdev[i % len(xdev)])
         barrier()
         torch.cuda.profiler.start()
-        ms = timed(wl, graphed, args.steps, 0)
+        ms = timed(wl, graphed, args.steps, 0, count=True)
         torch.cuda.profiler.stop()
     else:
-        ms = timed(wl, graphed, args.steps, args.warmup)
+        ms = timed(wl, graphed, args.steps, args.warmup, count=True)
     launches = KernelStats.launches
     KernelStats.reset(enabled=False)
 

@@ -168,7 +168,9 @@ __global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 16 ? 4 : (NV * EP
 // dres_colsum / dx_colsum (optional, fp32 [C]): column sums over all rows of the residual-path gradient and of the
 // produced dx -- the gradients of the Linear biases on either side of this LayerNorm (swin_block.py:222,227: dx is
 // the gradient of `proj(...) + bias`, dres that of `mlp(...) + bias`), which saves two full reduction passes.
-template <typename T, int G, int NV, int EPV, int R>
+// PLAIN: no residual-path gradient and no column sums (the PatchMerging norm, down.py:44: rows of 384-1536 channels, where
+// the three extra per-column register arrays of the general kernel meant spills and one CTA per SM)
+template <typename T, int G, int NV, int EPV, int R, bool PLAIN = false>
 __global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 8 ? 4 : (NV * EPV * R <= 16 ? 2 : 1))) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
                                                             const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                             const float* __restrict__ rstd_in, const T* __restrict__ dres,
@@ -179,20 +181,24 @@ __global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 8 ? 4 : (NV * EPV
   extern __shared__ float red[];                        // [4][C]
   const int gl = threadIdx.x % G, gr = threadIdx.x / G;
   const int nvec = C / EPV;
-  const bool has_res = dres != nullptr;
-  const bool want_rs = dres_colsum != nullptr && has_res, want_xs = dx_colsum != nullptr;
+  const bool has_res = !PLAIN && dres != nullptr;
+  const bool want_rs = !PLAIN && dres_colsum != nullptr && has_res, want_xs = !PLAIN && dx_colsum != nullptr;
   for (int i = threadIdx.x; i < 4 * C; i += kLnThreads) red[i] = 0.f;
-  float gm[NV][EPV], ag[NV][EPV], ab[NV][EPV], ar[NV][EPV], ax[NV][EPV];
+  constexpr int NVX = PLAIN ? 1 : NV, EPX = PLAIN ? 1 : EPV, RX = PLAIN ? 1 : R;     // (PLAIN: the extra arrays are never touched)
+  float gm[NV][EPV], ag[NV][EPV], ab[NV][EPV], ar[NVX][EPX], ax[NVX][EPX];
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int vi = gl + k * G;
     if (vi < nvec) loadf<EPV>(gamma + vi * EPV, gm[k]);
 #pragma unroll
-    for (int e = 0; e < EPV; ++e) ag[k][e] = ab[k][e] = ar[k][e] = ax[k][e] = 0.f;
+    for (int e = 0; e < EPV; ++e) {
+      ag[k][e] = ab[k][e] = 0.f;
+      if constexpr (!PLAIN) ar[k][e] = ax[k][e] = 0.f;
+    }
   }
   const float invC = 1.f / (float)C;
   for (long base = (long)blockIdx.x * (GPB * R); base < rows; base += (long)gridDim.x * (GPB * R)) {
-    float d[R][NV][EPV], xv[R][NV][EPV], rs[R][NV][EPV];
+    float d[R][NV][EPV], xv[R][NV][EPV], rs[RX][NVX][EPX];
     float mean[R], rstd[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
@@ -204,11 +210,16 @@ __global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 8 ? 4 : (NV * EPV
       for (int k = 0; k < NV; ++k) {
         const int vi = gl + k * G;
 #pragma unroll
-        for (int e = 0; e < EPV; ++e) d[r][k][e] = xv[r][k][e] = rs[r][k][e] = 0.f;
+        for (int e = 0; e < EPV; ++e) {
+          d[r][k][e] = xv[r][k][e] = 0.f;
+          if constexpr (!PLAIN) rs[r][k][e] = 0.f;
+        }
         if (vi < nvec && live) {
           Vec<T, EPV>::load(dy + row * C + vi * EPV, d[r][k]);
           Vec<T, EPV>::load(x + row * C + vi * EPV, xv[r][k]);
-          if (has_res) Vec<T, EPV>::load(dres + row * C + vi * EPV, rs[r][k]);
+          if constexpr (!PLAIN) {
+            if (has_res) Vec<T, EPV>::load(dres + row * C + vi * EPV, rs[r][k]);
+          }
         }
       }
     }
@@ -241,9 +252,12 @@ __global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 8 ? 4 : (NV * EPV
           float o[EPV];
 #pragma unroll
           for (int e = 0; e < EPV; ++e) {
-            o[e] = rstd[r] * (d[r][k][e] - s1 - xv[r][k][e] * s2) + rs[r][k][e];
-            ar[k][e] += rs[r][k][e];
-            ax[k][e] += o[e];
+            o[e] = rstd[r] * (d[r][k][e] - s1 - xv[r][k][e] * s2);
+            if constexpr (!PLAIN) {
+              o[e] += rs[r][k][e];
+              ar[k][e] += rs[r][k][e];
+              ax[k][e] += o[e];
+            }
           }
           Vec<T, EPV>::store(dx + row * C + vi * EPV, o);
         }
@@ -258,7 +272,8 @@ __global__ void __launch_bounds__(kLnThreads, (NV * EPV * R <= 8 ? 4 : (NV * EPV
     const int vi = gl + k * G;
 #pragma unroll
     for (int e = 0; e < EPV; ++e) {
-      float a = ag[k][e], b = ab[k][e], c = ar[k][e], d = ax[k][e];
+      float a = ag[k][e], b = ab[k][e], c = 0.f, d = 0.f;
+      if constexpr (!PLAIN) { c = ar[k][e]; d = ax[k][e]; }
 #pragma unroll
       for (int o = G; o < 32; o <<= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -473,8 +488,6 @@ __global__ void __launch_bounds__(kLnThreads, R == 1 ? 3 : 2) ln_bwd_bulk_kernel
   ring.stages = kMaxStages / ring.nop / R;
   ring.rows = rows; ring.n_tiles = (rows + TR - 1) / TR;
   ring.src[0] = dy; ring.src[1] = x; ring.src[2] = dres;
-  float* red = reinterpret_cast<float*>(ln_sm + (size_t)ring.stages * ring.nop * ring.tile_bytes);      // [4][C]
-  for (int i = threadIdx.x; i < 4 * C; i += kLnThreads) red[i] = 0.f;
   if (threadIdx.x == 0) {
     for (int s = 0; s < ring.stages; ++s) ln_mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -570,19 +583,32 @@ __global__ void __launch_bounds__(kLnThreads, R == 1 ? 3 : 2) ln_bwd_bulk_kernel
       if (want_rs) c += __shfl_xor_sync(0xffffffffu, c, o);
       if (want_xs) d += __shfl_xor_sync(0xffffffffu, d, o);
     }
+    // per-warp partial sums -> the (now idle) ring memory, [warp][array][C]: plain stores.  (fp32 shared-memory atomics
+    // are compare-and-swap loops; 8 warps contending for every column made this epilogue a fixed ~5 us per CTA, a quarter
+    // of the kernel at the late stages' row counts.)
     if ((threadIdx.x & 31) < G && lane_live) {
-      atomicAdd(&red[gl * EPV + e], a);
-      atomicAdd(&red[C + gl * EPV + e], b);
-      if (want_rs) atomicAdd(&red[2 * C + gl * EPV + e], c);
-      if (want_xs) atomicAdd(&red[3 * C + gl * EPV + e], d);
+      float* part = reinterpret_cast<float*>(ln_sm) + (size_t)(threadIdx.x >> 5) * 4 * C;
+      part[gl * EPV + e] = a;
+      part[C + gl * EPV + e] = b;
+      if (want_rs) part[2 * C + gl * EPV + e] = c;
+      if (want_xs) part[3 * C + gl * EPV + e] = d;
     }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < C; i += kLnThreads) {
-    atomicAdd(&dgamma[i], red[i]);
-    atomicAdd(&dbeta[i], red[C + i]);
-    if (want_rs) atomicAdd(&dres_colsum[i], red[2 * C + i]);
-    if (want_xs) atomicAdd(&dx_colsum[i], red[3 * C + i]);
+    const float* part = reinterpret_cast<const float*>(ln_sm);
+    float a = 0.f, b = 0.f, c = 0.f, d = 0.f;
+#pragma unroll
+    for (int w = 0; w < kLnThreads / 32; ++w) {
+      a += part[(w * 4 + 0) * C + i];
+      b += part[(w * 4 + 1) * C + i];
+      if (want_rs) c += part[(w * 4 + 2) * C + i];
+      if (want_xs) d += part[(w * 4 + 3) * C + i];
+    }
+    atomicAdd(&dgamma[i], a);
+    atomicAdd(&dbeta[i], b);
+    if (want_rs) atomicAdd(&dres_colsum[i], c);
+    if (want_xs) atomicAdd(&dx_colsum[i], d);
   }
 }
 
@@ -605,14 +631,28 @@ template <typename T, int G, int NV, int EPV, int R>
 static int ln_launch(bool fwd, const LnArgs& a, cudaStream_t st) {
   constexpr int GPB = kLnThreads / G;
   long blocks = (a.rows + GPB * R - 1) / (GPB * R);
-  // backward: fewer CTAs -> fewer global atomics
-  const long cap = 148L * (fwd ? env_int("PWA_LN_CAPF", 8) : env_int("PWA_LN_CAPB", 4));
+  // backward: fewer CTAs -> fewer global atomics; with few rows (the late PatchMerging norms: 7 K rows of 768 channels) every
+  // CTA should also run several iterations, or its epilogue (4C shared words zeroed, 2C..4C shared + global atomics)
+  // outweighs its share of the rows: 48 -> see tools/bench_ln.py
+  long cap = 148L * (fwd ? env_int("PWA_LN_CAPF", 8) : env_int("PWA_LN_CAPB", 4));
+  if (!fwd) {
+    const long few = blocks / 6 > 148 ? blocks / 6 : (blocks < 148 ? blocks : 148);
+    if (few < cap) cap = few;
+  }
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   if (fwd) {
     ln_fwd_kernel<T, G, NV, EPV, R><<<(unsigned)blocks, kLnThreads, 0, st>>>((const T*)a.a, (const T*)a.res, a.gamma, a.bm,
                                                                               (T*)a.o1, (T*)a.o2, a.f1, a.f2, a.rows, a.C, a.eps);
   } else {
+    if constexpr (NV >= 2) {
+      if (a.res == nullptr && a.f3 == nullptr && a.f4 == nullptr) {
+        ln_bwd_kernel<T, G, NV, EPV, R, true><<<(unsigned)blocks, kLnThreads, 4 * a.C * sizeof(float), st>>>(
+            (const T*)a.a, (const T*)a.b, a.gamma, a.bm, a.rstd, nullptr, (T*)a.o1, a.f1, a.f2, nullptr, nullptr, a.rows, a.C);
+        PWA_CUDA_OK(cudaGetLastError());
+        return PWA_OK;
+      }
+    }
     ln_bwd_kernel<T, G, NV, EPV, R><<<(unsigned)blocks, kLnThreads, 4 * a.C * sizeof(float), st>>>(
         (const T*)a.a, (const T*)a.b, a.gamma, a.bm, a.rstd, (const T*)a.res, (T*)a.o1, a.f1, a.f2, a.f3, a.f4, a.rows, a.C);
   }
@@ -625,7 +665,8 @@ static int ln_launch_bulk_r(bool fwd, const LnArgs& a, cudaStream_t st) {
   using T = __nv_bfloat16;
   constexpr int TR = kLnThreads / G * R;
   const int nop = fwd ? (a.res ? 2 : 1) : (a.res ? 3 : 2);
-  const size_t smem = (size_t)(kMaxStages / nop / R) * nop * TR * a.C * 2 + (fwd ? 0 : 4 * a.C * sizeof(float));
+  // (backward epilogue: the per-warp column sums, 8 x 4 x C floats, reuse the ring memory: >= 192 * C bytes for every G, R)
+  const size_t smem = (size_t)(kMaxStages / nop / R) * nop * TR * a.C * 2;
   long blocks = (a.rows + TR - 1) / TR;
   // (backward: 3 CTAs/SM = 85 registers, no spills; the bytes in flight no longer depend on the occupancy)
   const long cap = 148L * (fwd ? env_int("PWA_LN_BULK_CTAS_F", R == 1 ? 4 : 3) : env_int("PWA_LN_BULK_CTAS_B", R == 1 ? 3 : 2));

@@ -25,7 +25,7 @@ def graph_time(fn, reps=20):
     return e0.elapsed_time(e1) / (2 * reps) * 1e3
 
 env = {k: os.environ.get(k) for k in ("PWA_LN_RF", "PWA_LN_RB", "PWA_LN_EPV", "PWA_LN_CAPF", "PWA_LN_CAPB") if os.environ.get(k)}
-for rows, Cc in ((4 * 432 * 256, 48), (4 * 54 * 256, 96), (4 * 28 * 256, 192), (4 * 13824, 384)):
+for rows, Cc in ((4 * 432 * 256, 48), (4 * 54 * 256, 96), (4 * 28 * 256, 192), (4 * 13824, 384), (4 * 1728, 768)):
     dt = torch.bfloat16
     mk = lambda: [torch.randn(rows, Cc, device=dev).to(dt) for _ in range(NB)]
     x, r, s_, y, dy, dx = mk(), mk(), mk(), mk(), mk(), mk()

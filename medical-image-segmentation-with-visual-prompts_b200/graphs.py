@@ -26,9 +26,12 @@ class GraphedStep:
         """step_fn(*inputs) must run forward AND backward and return a (scalar) loss tensor; it is called `warmup`
         times eagerly on a side stream (lazy initialisation: cuBLAS handles, kernel attributes, cached index maps),
         then once more under capture.  Inputs that require grad get a static .grad too (`input_grads`).
-        flat_grads=True makes every parameter's .grad a view into ONE flat fp32 buffer (`flat_grad`, zeroed inside the
-        graph at the start of each step), so that the data-parallel exchange is a single in-place all-reduce of that
-        buffer with no gather / scatter copies (`allreduce_flat`)."""
+        flat_grads=True makes every parameter's .grad a view into ONE flat fp32 buffer (`flat_grad`), so that the
+        data-parallel exchange is a single in-place all-reduce of that buffer (`allreduce_flat`).  Inside the graph the
+        backward produces its gradients as usual (autograd hands the freshly computed tensors over without a kernel) and
+        ONE multi-tensor copy at the end of the step moves them into the flat buffer.  (Pointing .grad at the views during
+        the backward instead made autograd ACCUMULATE into them: one tiny add kernel per parameter, ~150 launches and
+        0.1-0.2 ms per step -- most of what the 2/4/8-GPU lines lost against one GPU.)"""
         if not example_inputs or not all(t.is_cuda for t in example_inputs):
             raise RuntimeError("GraphedStep: CUDA tensors only (pwa_b200 has no CPU path)")
         self.params: List[torch.nn.Parameter] = [p for p in params]
@@ -48,8 +51,11 @@ class GraphedStep:
             inner = step_fn
 
             def step_fn(*inputs):
-                self.flat_grad.zero_()
-                return inner(*inputs)
+                loss = inner(*inputs)
+                pairs = [(v, p.grad) for p, v in zip(self.params, self._grad_views) if p.grad is not None]
+                with torch.no_grad():               # (parameters the step never reaches keep their zeros)
+                    torch._foreach_copy_([v for v, _ in pairs], [g for _, g in pairs])
+                return loss
         # CUDA events cannot be recorded inside a capture; launches are counted during the capture pass
         saved = (KernelStats.enabled, KernelStats.timing, KernelStats.launches)
         KernelStats.enabled, KernelStats.timing = True, False
@@ -69,17 +75,15 @@ class GraphedStep:
                 self.loss = step_fn(*self.static_inputs)
             self.launches_per_replay = KernelStats.launches - launches0   # pwa kernels inside one replay
             # the tensors every replay writes the parameter gradients into (None for parameters the step never reaches)
-            self.static_grads = [p.grad for p in self.params]
+            self.static_grads = [p.grad for p in self.params] if self.flat_grad is None else list(self._grad_views)
+            if self.flat_grad is not None:
+                self.bind_grads()
         finally:
             KernelStats.enabled, KernelStats.timing, KernelStats.launches = saved
 
     def _zero(self):
-        if self.flat_grad is not None:
-            for p, v in zip(self.params, self._grad_views):
-                p.grad = v                      # autograd accumulates in place into the flat buffer
-        else:
-            for p in self.params:
-                p.grad = None
+        for p in self.params:
+            p.grad = None
         for t in self.static_inputs:
             t.grad = None
 

@@ -167,10 +167,11 @@ class EncoderWorkload:
     def step(self, x):
         b = x.shape[0]
         loss = 0.0
+        ps = [self.prompts[k].to(x.dtype).unsqueeze(0).expand(b, -1, -1) for k in range(2 * len(self.model))]
+        for j, stage in enumerate(self.model):      # (what SwinUnetR.forward does at its top: feature-map-independent inputs
+            stage.prefetch_side_inputs((ps[2 * j], ps[2 * j + 1]), x)     # of every stage start on the side stream now)
         for j, stage in enumerate(self.model):
-            p_w = self.prompts[2 * j].to(x.dtype).unsqueeze(0).expand(b, -1, -1)
-            p_sw = self.prompts[2 * j + 1].to(x.dtype).unsqueeze(0).expand(b, -1, -1)
-            x = stage(x, (p_w, p_sw))
+            x = stage(x, (ps[2 * j], ps[2 * j + 1]))
             loss = loss + _MeanSquare.apply(x)          # every stage output feeds the decoder / heads in the real model
         loss.backward()
         return loss.detach()

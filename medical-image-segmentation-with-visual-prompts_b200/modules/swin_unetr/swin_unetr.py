@@ -117,10 +117,15 @@ class SwinUnetR(nn.Module):
     def forward_swin_transformer(self, x):
         """out_vit = [deepest stage output, ..., stage-0 output, patch embedding, x] (reference :46-63)."""
         outs = [x]
+        # what the stages need besides the feature map (bias tables, packed weights, prompt K|V) depends on parameters only:
+        # under graph capture all stages start computing it on the side stream now, under the patch embedding
+        ps = [self._prompts('enc', j, x.size(0), self.conf.use_encoder_prompting) for j in range(self.conf.depth_unet)]
+        for j in range(self.conf.depth_unet):
+            self.encoder_blocks[j].prefetch_side_inputs(ps[j], x)
         enc = self.input_layer(x)
         outs.insert(0, enc)
         for j in range(self.conf.depth_unet):
-            enc = self.encoder_blocks[j](enc, self._prompts('enc', j, enc.size(0), self.conf.use_encoder_prompting))
+            enc = self.encoder_blocks[j](enc, ps[j])
             outs.insert(0, enc)
         return {'out_vit': outs}
 

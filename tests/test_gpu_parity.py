@@ -713,6 +713,8 @@ def test_graphed_step_matches_eager(flat):
 
     def step(x):
         p = tuple(t.to(x.dtype).unsqueeze(0).expand(x.shape[0], -1, -1) for t in prompts)
+        if flat:                        # (one of the two runs also takes the prefetched side inputs)
+            pair.prefetch_side_inputs(p, x)
         loss = pair(x, p).float().square().mean()
         loss.backward()
         return loss.detach()

@@ -774,7 +774,8 @@ def test_colsum_rows_matches_float64(T, C, dtype):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("T,co,ci", [(72 * 512, 48, 48), (64 * 448, 144, 48), (16384 + 8, 96, 96), (1000, 48, 48)])
+@pytest.mark.parametrize("T,co,ci", [(72 * 512, 48, 48), (64 * 448, 144, 48), (16384 + 8, 96, 96), (1000, 48, 48),
+                                     (28672, 576, 192), (13824, 192, 384), (3456, 384, 768)])
 def test_token_split_weight_gradient(T, co, ci):
     """The batched token-split dW = dy^T x (bf16 operands, fp32 partials) against an fp64 GEMM; shapes that do not split
     (no divisor of T in range, too few tokens) take the single-GEMM path."""

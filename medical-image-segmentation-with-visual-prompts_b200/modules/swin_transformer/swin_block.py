@@ -60,15 +60,17 @@ class _SideInputs:
     kernels; `ConsecutiveSwinBlocks` computes them for both blocks on a side stream, where they overlap the partition /
     LayerNorm / projection kernels of the main chain (a captured step keeps them as a parallel graph branch, and
     autograd runs their backward on the same side stream).  `ready` is recorded on that stream after the last of them."""
-    __slots__ = ("tables", "lowp", "kvp", "ready")
+    __slots__ = ("tables", "lowp", "kvp", "seed", "ready")
 
-    def __init__(self, tables, lowp, kvp, ready=None):
-        self.tables, self.lowp, self.kvp, self.ready = tables, lowp, kvp, ready
+    def __init__(self, tables, lowp, kvp, seed=None, ready=None):
+        self.tables, self.lowp, self.kvp, self.seed, self.ready = tables, lowp, kvp, seed, ready
 
     def tensors(self):
         out = [t for t in self.tables if t is not None] + [self.lowp['qkv']._base]
         if self.kvp is not None:
             out.append(self.kvp)
+        if self.seed is not None:
+            out.append(self.seed)
         return out
 
 
@@ -249,7 +251,12 @@ class SwinTransformerBlock(nn.Module):
                 raise ValueError(f"SwinTransformerBlock: prompt tokens must be [B, I, {c}], got {tuple(p.shape)}")
             prompts = PF.layer_norm(p.to(cdt), self.attn_norm.weight, self.attn_norm.bias, 1e-6)
             kvp = self.attn.project_prompts(prompts, lowp)
-        return _SideInputs(tables, lowp, kvp)
+        # the four dropout seed words of this forward (attention, projection): one tiny RNG launch that belongs on the side
+        # branch as well, and outside every checkpointed region
+        seed = None
+        if self.training and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):
+            seed = PF.new_dropout_seed(tables[0].device, 4)
+        return _SideInputs(tables, lowp, kvp, seed)
 
     def _use_token_gemm(self, c, rows, dtype):
         return (PF.layer_norm_supported(c) and PF.token_gemm_supported(c, 3 * c, dtype) and not _NO_TOKEN_GEMM
@@ -312,8 +319,8 @@ class SwinTransformerBlock(nn.Module):
                                       "4, at most 2048); there is no torch fallback")
         if side is None:
             side = self._side_inputs(p, cdt, c)
-        if self.training and drop_seed is None and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):
-            drop_seed = PF.new_dropout_seed(xw.device, 4)
+        if drop_seed is None:
+            drop_seed = side.seed
         run = ((lambda fn, *a: checkpoint.checkpoint(fn, *a, use_reentrant=False, preserve_rng_state=False)) if ckpt
                else (lambda fn, *a: fn(*a)))
         xw, qkv = run(self._seg_pre, xw, cdt, side)
@@ -331,9 +338,9 @@ class SwinTransformerBlock(nn.Module):
         segments around it; 'full' recomputes the whole token pipeline of the block, attention included."""
         if not (self.use_checkpoint and torch.is_grad_enabled()):
             return self._tokens_forward(xw, p, geom, cdt, None, side)
-        seed = None
-        if self.training and (self.attn.attn_drop.p > 0 or self.attn.proj_drop.p > 0):
-            seed = PF.new_dropout_seed(xw.device, 4)
+        if side is None:
+            side = self._side_inputs(p, cdt, xw.shape[-1])
+        seed = side.seed
         if self.checkpoint_policy == 'selective':
             return self._tokens_forward(xw, p, geom, cdt, seed, side, True)
         return checkpoint.checkpoint(self._tokens_forward, xw, p, geom, cdt, seed, side, use_reentrant=False,

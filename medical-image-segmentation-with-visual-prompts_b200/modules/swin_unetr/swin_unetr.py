@@ -147,10 +147,16 @@ class SwinUnetR(nn.Module):
 
     def forward_decoder(self, c):
         conf = self.conf
+        # (as in forward_swin_transformer: the decoder stages' feature-map-independent inputs start on the side stream now)
+        ps = [self._prompts('dec', j, c[0].size(0), conf.use_decoder_prompting) for j in range(conf.depth_unet)]
+        for j in range(conf.depth_unet):
+            swin = getattr(self.decoder_blocks[j], 'swin_layer', None)
+            if swin is not None:
+                swin.prefetch_side_inputs(ps[j], c[0])
         dec = self.bottleneck(c[0]) + c[0]
         for j in range(conf.depth_unet):
             res = self.residual_blocks[j](c[j + 1])
-            dec = self.decoder_blocks[j](dec, res, self._prompts('dec', j, dec.size(0), conf.use_decoder_prompting))
+            dec = self.decoder_blocks[j](dec, res, ps[j])
         if conf.unetr_res_block == 'none':
             out = self.output_layer(dec)
         else:
